@@ -1,0 +1,312 @@
+// Coarse-to-fine alignment kernels for sm_100a: gradients + tile Hessians, flow upscaling, L2 block matching,
+// the "L1" level as the compiled reference executes it, and inverse-compositional Lucas-Kanade (ICA).
+//
+// Replaces handheld_super_resolution/ICA.py:15-76 (init_ica: two F.conv2d + compute_hessian, one thread per
+// tile), alignment.py:150-172 (upscale_lvl), block_matching.py:20-76,348-378 (gather + batched rFFT/irFFT +
+// box-filter conv2d + argmin), block_matching.py:78-345 (cuda_L1_local_search*) and ICA.py:78-481
+// (ica_kernel_{8,16,32,64}).  One CTA per tile; tiles and search windows are staged in shared memory, SSD sums
+// are reduced with warp shuffles.
+#include "common.cuh"
+
+namespace hhsr {
+
+// ---------------------------------------------------------------------------------------------------------
+// gradients + Hessian: one CTA per ts x ts cell of ceil(h/ts) x ceil(w/ts); complete tiles also emit H.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grad_hessian_kernel(const float *__restrict__ img, int h, int w, int ts, int ny,
+                                                           int nx, float *__restrict__ gradx, float *__restrict__ grady,
+                                                           float *__restrict__ hessian) {
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    float h00 = 0.f, h01 = 0.f, h11 = 0.f;
+    for (int p = threadIdx.x; p < ts * ts; p += blockDim.x) {
+        const int y = ty * ts + p / ts, x = tx * ts + p % ts;
+        if (y >= h || x >= w) continue;
+        const float l = x > 0 ? __ldg(img + (size_t)y * w + x - 1) : 0.f;       // zero 'same' padding, ICA.py:20-21
+        const float r = x < w - 1 ? __ldg(img + (size_t)y * w + x + 1) : 0.f;
+        const float u = y > 0 ? __ldg(img + (size_t)(y - 1) * w + x) : 0.f;
+        const float d = y < h - 1 ? __ldg(img + (size_t)(y + 1) * w + x) : 0.f;
+        const float gx = r - l, gy = d - u;
+        gradx[(size_t)y * w + x] = gx;
+        grady[(size_t)y * w + x] = gy;
+        h00 = fmaf(gx, gx, h00), h01 = fmaf(gx, gy, h01), h11 = fmaf(gy, gy, h11);
+    }
+    if (ty >= ny || tx >= nx) return;   // uniform per CTA
+    __shared__ float red[3][8];
+    h00 = warp_sum(h00), h01 = warp_sum(h01), h11 = warp_sum(h11);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red[0][warp] = h00, red[1][warp] = h01, red[2][warp] = h11;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += red[0][k], b += red[1][k], c += red[2][k];
+        reinterpret_cast<float4 *>(hessian)[(size_t)ty * nx + tx] = make_float4(a, b, b, c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// flow upscaling (alignment.py:150-172); bilinear / bicubic follow torch F.interpolate(align_corners=False)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+__global__ void upscale_flow_kernel(const float2 *__restrict__ in, int ny_in, int nx_in, float2 *__restrict__ out, int ny_out,
+                                    int nx_out, int rep, float factor, int mode) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nx_out || y >= ny_out) return;
+    float2 v = make_float2(0.f, 0.f);
+    if (y < ny_in * rep && x < nx_in * rep) {
+        if (mode == 0) {
+            v = in[(size_t)(y / rep) * nx_in + x / rep];
+        } else {
+            const float sc = 1.0f / (float)rep;
+            float sy = sc * ((float)y + 0.5f) - 0.5f, sx = sc * ((float)x + 0.5f) - 0.5f;
+            if (mode == 1) {
+                sy = fmaxf(sy, 0.f), sx = fmaxf(sx, 0.f);
+                const int y0 = (int)sy, x0 = (int)sx;
+                const int y1 = min(y0 + 1, ny_in - 1), x1 = min(x0 + 1, nx_in - 1);
+                const float ly = sy - (float)y0, lx = sx - (float)x0;
+                const float2 a = in[(size_t)y0 * nx_in + x0], b = in[(size_t)y0 * nx_in + x1];
+                const float2 c = in[(size_t)y1 * nx_in + x0], d = in[(size_t)y1 * nx_in + x1];
+                v.x = (1.f - ly) * ((1.f - lx) * a.x + lx * b.x) + ly * ((1.f - lx) * c.x + lx * d.x);
+                v.y = (1.f - ly) * ((1.f - lx) * a.y + lx * b.y) + ly * ((1.f - lx) * c.y + lx * d.y);
+            } else {
+                const float A = -0.75f;
+                const float fy = floorf(sy), fx = floorf(sx);
+                const float ty = sy - fy, tx = sx - fx;
+                const float wy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+                const float wx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+                float ax = 0.f, ay = 0.f;
+                for (int i = 0; i < 4; ++i) {
+                    const int yy = min(max((int)fy - 1 + i, 0), ny_in - 1);
+                    float rx = 0.f, ry = 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        const int xx = min(max((int)fx - 1 + j, 0), nx_in - 1);
+                        const float2 q = in[(size_t)yy * nx_in + xx];
+                        rx += wx[j] * q.x, ry += wx[j] * q.y;
+                    }
+                    ax += wy[i] * rx, ay += wy[i] * ry;
+                }
+                v = make_float2(ax, ay);
+            }
+        }
+        v.x *= factor, v.y *= factor;
+    }
+    out[(size_t)y * nx_out + x] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// L2 block matching.  E(v,u) = sum m^2 - 2 sum ref*m, accumulated in float64 so the argmin is the exact one
+// (the reference obtains the same quantity through float32 FFTs; only exact/near ties can differ).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ ref, int ref_w, const float *__restrict__ mov,
+                                                    int mov_h, int mov_w, float2 *__restrict__ flow, int nx, int ts, int r) {
+    extern __shared__ float bsm[];
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int sw = ts + 2 * r, n = 2 * r + 1;
+    float *s_ref = bsm, *s_win = bsm + ts * ts;
+    double *s_err = reinterpret_cast<double *>(bsm + ts * ts + ((sw * sw + 1) & ~1));
+    const float2 f = flow[(size_t)ty * nx + tx];
+    const int fx = (int)rintf(f.x), fy = (int)rintf(f.y);                       // flow.round(), :352
+    for (int p = threadIdx.x; p < ts * ts; p += blockDim.x)
+        s_ref[p] = __ldg(ref + (size_t)(ty * ts + p / ts) * ref_w + tx * ts + p % ts);
+    for (int p = threadIdx.x; p < sw * sw; p += blockDim.x) {
+        const int yy = min(max(ty * ts + fy - r + p / sw, 0), mov_h - 1);       // clamp, :368-369
+        const int xx = min(max(tx * ts + fx - r + p % sw, 0), mov_w - 1);
+        s_win[p] = __ldg(mov + (size_t)yy * mov_w + xx);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int s = warp; s < n * n; s += nwarps) {
+        const int v = s / n, u = s % n;
+        double e = 0.0;
+        for (int p = lane; p < ts * ts; p += 32) {
+            const int y = p / ts, x = p % ts;
+            const double m = (double)s_win[(y + v) * sw + x + u];
+            e += m * m - 2.0 * (double)s_ref[p] * m;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if (lane == 0) s_err[s] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0;
+        double be = s_err[0];
+        for (int s = 1; s < n * n; ++s)
+            if (s_err[s] < be) be = s_err[s], best = s;                          // first minimum, torch.argmin
+        flow[(size_t)ty * nx + tx] = make_float2(f.x + (float)(best % n - r), f.y + (float)(best / n - r));
+    }
+}
+
+__global__ void bm_l1_compat_kernel(float *__restrict__ flow, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flow[i] = rintf(flow[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ICA.  MODE 0: ts = 8 (clamped sampling, float64 1/det); MODE 1: ts = 16, 32 (zero fill);
+// MODE 2: ts = 64 (zero fill, rows as read by the reference's sliding window — SURVEY Q4).
+// PPT = pixels per thread, NT threads per tile.
+// ---------------------------------------------------------------------------------------------------------
+template <int TS, int MODE, int NT>
+__global__ void __launch_bounds__(NT) ica_kernel(const float *__restrict__ ref, const float *__restrict__ gradx,
+                                                 const float *__restrict__ grady, int ref_w, const float4 *__restrict__ hessian,
+                                                 const float *__restrict__ mov, int h, int w, float2 *__restrict__ flow, int nx,
+                                                 int n_iter) {
+    constexpr int PPT = TS * TS / NT;
+    const int px = blockIdx.x, py = blockIdx.y, tid = threadIdx.x;
+    const float4 Hm = __ldg(hessian + (size_t)py * nx + px);
+    const float A00 = Hm.x, A01 = Hm.y, A10 = Hm.z, A11 = Hm.w;
+    const float det = A00 * A11 - A01 * A10;
+    float det_inv_f = 0.f;
+    double det_inv_d = 0.0;
+    if (MODE == 0) {
+        if (fabs((double)det) < 1e-10) return;                                  // ICA.py:124-126
+        det_inv_d = 1.0 / (double)det;
+    } else {
+        if (fabsf(det) < 1e-10f) return;
+        det_inv_f = 1.0f / det;
+    }
+    __shared__ float s_flow[2];
+    __shared__ float s_red[2][NT / 32];
+    if (tid == 0) {
+        const float2 f = flow[(size_t)py * nx + px];
+        s_flow[0] = f.x, s_flow[1] = f.y;
+    }
+    float rc[PPT], gx[PPT], gy[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int p = tid + k * NT;
+        const size_t o = (size_t)(py * TS + p / TS) * ref_w + px * TS + p % TS;
+        rc[k] = __ldg(ref + o), gx[k] = __ldg(gradx + o), gy[k] = __ldg(grady + o);
+    }
+    for (int it = 0; it < n_iter; ++it) {
+        __syncthreads();
+        const float ax = s_flow[0], ay = s_flow[1];
+        const int ix = (int)ax, iy = (int)ay;                                   // trunc toward zero
+        const float frx = ax - truncf(ax), fry = ay - truncf(ay);              // signed modf
+        float B0 = 0.f, B1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int p = tid + k * NT;
+            const int ly = p / TS, lx = p % TS;
+            const int X = px * TS + lx + ix;
+            int Yt = py * TS + ly + iy, Yb = 0;
+            float m00, m01, m10, m11;
+            if (MODE == 0) {
+                const int Xf = min(max(X, 0), w - 1), Yf = min(max(Yt, 0), h - 1);
+                const int Xc = min(max(Xf + 1, 0), w - 1), Yc = min(max(Yf + 1, 0), h - 1);
+                m00 = __ldg(mov + (size_t)Yf * w + Xf), m01 = __ldg(mov + (size_t)Yf * w + Xc);
+                m10 = __ldg(mov + (size_t)Yc * w + Xf), m11 = __ldg(mov + (size_t)Yc * w + Xc);
+            } else {
+                if (MODE == 2) {
+                    const int i_in = ly & 3;                 // ICA.py:441-445
+                    const int Ybase = Yt - i_in;
+                    Yt = (i_in == 0) ? Ybase : Ybase + i_in + 1;
+                    Yb = Ybase + i_in + 2;
+                } else {
+                    Yb = Yt + 1;
+                }
+                const bool x0 = X >= 0 && X < w, x1 = X + 1 >= 0 && X + 1 < w;
+                const bool yt = Yt >= 0 && Yt < h, yb = Yb >= 0 && Yb < h;
+                m00 = (yt && x0) ? __ldg(mov + (size_t)Yt * w + X) : 0.f;
+                m01 = (yt && x1) ? __ldg(mov + (size_t)Yt * w + X + 1) : 0.f;
+                m10 = (yb && x0) ? __ldg(mov + (size_t)Yb * w + X) : 0.f;
+                m11 = (yb && x1) ? __ldg(mov + (size_t)Yb * w + X + 1) : 0.f;
+            }
+            const float top = m00 + (m01 - m00) * frx;
+            const float bot = m10 + (m11 - m10) * frx;
+            const float gt = (top + (bot - top) * fry) - rc[k];
+            B0 += -gx[k] * gt;
+            B1 += -gy[k] * gt;
+        }
+        B0 = warp_sum(B0), B1 = warp_sum(B1);
+        if ((tid & 31) == 0) s_red[0][tid >> 5] = B0, s_red[1][tid >> 5] = B1;
+        __syncthreads();
+        if (tid == 0) {
+            float b0 = s_red[0][0], b1 = s_red[1][0];
+            for (int k = 1; k < NT / 32; ++k) b0 += s_red[0][k], b1 += s_red[1][k];
+            if (MODE == 0) {
+                s_flow[0] = (float)((double)s_flow[0] + det_inv_d * (double)(A11 * b0 - A01 * b1));
+                s_flow[1] = (float)((double)s_flow[1] + det_inv_d * (double)(-A10 * b0 + A00 * b1));
+            } else {
+                s_flow[0] += det_inv_f * (A11 * b0 - A01 * b1);
+                s_flow[1] += det_inv_f * (-A10 * b0 + A00 * b1);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) flow[(size_t)py * nx + px] = make_float2(s_flow[0], s_flow[1]);
+}
+
+}  // namespace hhsr
+
+using namespace hhsr;
+
+extern "C" int hhsr_grad_hessian(const float *img, int h, int w, int ts, float *gradx, float *grady, float *hessian,
+                                 hhsr_stream_t stream) {
+    HHSR_REQUIRE(img && gradx && grady && hessian, "null pointer");
+    HHSR_REQUIRE(h > 0 && w > 0 && ts > 0, "non-positive size");
+    HHSR_REQUIRE((uintptr_t)hessian % 16 == 0, "hessian must be 16-byte aligned");
+    const int ny = h / ts, nx = w / ts;
+    dim3 grid(ceil_div(w, ts), ceil_div(h, ts));
+    const int nt = ts * ts >= 256 ? 256 : 64;
+    grad_hessian_kernel<<<grid, nt, 0, (cudaStream_t)stream>>>(img, h, w, ts, ny, nx, gradx, grady, hessian);
+    return launch_status("grad_hessian");
+}
+
+extern "C" int hhsr_upscale_flow(const float *flow_in, int ny_in, int nx_in, float *flow_out, int ny_out, int nx_out,
+                                 int repeat, float factor, int mode, hhsr_stream_t stream) {
+    HHSR_REQUIRE(flow_in && flow_out, "null pointer");
+    HHSR_REQUIRE(ny_in > 0 && nx_in > 0 && ny_out > 0 && nx_out > 0 && repeat >= 1, "non-positive size");
+    HHSR_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (nearest), 1 (bilinear) or 2 (bicubic)");
+    dim3 block(16, 16), grid(ceil_div(nx_out, 16), ceil_div(ny_out, 16));
+    upscale_flow_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(flow_in), ny_in, nx_in,
+                                                                 reinterpret_cast<float2 *>(flow_out), ny_out, nx_out, repeat,
+                                                                 factor, mode);
+    return launch_status("upscale_flow");
+}
+
+extern "C" int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const float *mov, int mov_h, int mov_w,
+                                 float *flow, int ny, int nx, int ts, int radius, hhsr_stream_t stream) {
+    HHSR_REQUIRE(ref && mov && flow, "null pointer");
+    HHSR_REQUIRE(ny > 0 && nx > 0 && mov_h > 0 && mov_w > 0, "non-positive size");
+    if (!(ts == 8 || ts == 16 || ts == 32 || ts == 64))
+        return unsupported("L2 block matching tile size must be 8, 16, 32 or 64 (block_matching.py:48-57)");
+    HHSR_REQUIRE(radius >= 0 && radius <= 8, "search radius must be in [0, 8]");
+    HHSR_REQUIRE(ny * ts <= ref_h && nx * ts <= ref_w, "tile grid exceeds the reference level");
+    const int sw = ts + 2 * radius, n = 2 * radius + 1;
+    const size_t smem = (size_t)(ts * ts + ((sw * sw + 1) & ~1)) * sizeof(float) + (size_t)n * n * sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(bm_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(nx, ny);
+    bm_l2_kernel<<<grid, ts >= 16 ? 256 : 64, smem, (cudaStream_t)stream>>>(ref, ref_w, mov, mov_h, mov_w,
+                                                                           reinterpret_cast<float2 *>(flow), nx, ts, radius);
+    return launch_status("bm_l2_search");
+}
+
+extern "C" int hhsr_bm_l1_compat(float *flow, int n, hhsr_stream_t stream) {
+    HHSR_REQUIRE(flow && n > 0, "null pointer or empty flow");
+    bm_l1_compat_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(flow, n);
+    return launch_status("bm_l1_compat");
+}
+
+extern "C" int hhsr_ica(const float *ref, const float *gradx, const float *grady, int ref_h, int ref_w,
+                        const float *hessian, const float *mov, int mov_h, int mov_w, float *flow, int ny, int nx, int ts,
+                        int n_iter, hhsr_stream_t stream) {
+    HHSR_REQUIRE(ref && gradx && grady && hessian && mov && flow, "null pointer");
+    HHSR_REQUIRE(ny > 0 && nx > 0 && mov_h > 0 && mov_w > 0 && n_iter > 0, "non-positive size");
+    HHSR_REQUIRE(ny * ts <= ref_h && nx * ts <= ref_w, "tile grid exceeds the reference level");
+    HHSR_REQUIRE((uintptr_t)hessian % 16 == 0 && (uintptr_t)flow % 8 == 0, "hessian/flow misaligned");
+    dim3 grid(nx, ny);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float4 *H4 = reinterpret_cast<const float4 *>(hessian);
+    float2 *F2 = reinterpret_cast<float2 *>(flow);
+    switch (ts) {
+        case 8: ica_kernel<8, 0, 64><<<grid, 64, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter); break;
+        case 16: ica_kernel<16, 1, 256><<<grid, 256, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter); break;
+        case 32: ica_kernel<32, 1, 256><<<grid, 256, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter); break;
+        case 64: ica_kernel<64, 2, 256><<<grid, 256, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter); break;
+        default: return unsupported("ICA kernel for this tile size not implemented (ICA.py:100)");
+    }
+    return launch_status("ica");
+}

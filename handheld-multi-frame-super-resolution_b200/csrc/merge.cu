@@ -1,0 +1,365 @@
+// Kernel-regression merge (Alg. 4 and Alg. 11 of the IPOL paper) for sm_100a.
+//
+// Replaces handheld_super_resolution/merge.py:82-233 (accumulate_ref) and :290-434 (accumulate), plus
+// utils.py:62-120 (divide, add).  HBM-bound: per comp frame the accumulators num/den [Hs][Ws][3] f32 are read and
+// written once (48 B per HR pixel) and raw/r/covariances are read once (12 B per LR pixel) — see DESIGN.md.
+//
+// Layout / mapping: one thread owns VEC=4 consecutive HR pixels of one row, so its slice of each accumulator is
+// 12 consecutive floats = 3 x float4 (the [.,.,3] interleaving is part of the boundary: main() returns it).
+// LR-side gathers (raw 3x3 taps, 4 covariance quads, r, tile flow) go through the read-only L1/L2 path; they
+// are reused ~36x across neighbouring HR pixels.
+//
+// Arithmetic: the reference does all position/weight math in float64 by accident.  Here the
+// sub-pixel position is formed exactly as the reference does it (float64: (hr+0.5)/scale + flow, truncation),
+// then reduced to tap-relative float32 offsets; weights are float32 with ex2.approx.  merge_ref runs once per
+// burst and keeps the reference's float64 arithmetic literally.
+#include "common.cuh"
+
+namespace hhsr {
+
+struct MergeFrame {
+    const float *raw, *flow, *covs, *r;
+};
+constexpr int kMaxBatch = 24;
+struct MergeBatch {
+    MergeFrame f[kMaxBatch];
+    int K;
+};
+struct MergeGeom {
+    int H, W, nx, ts, ch, cw, Hs, Ws, cfa;
+    double scale;
+};
+
+// Contribution of one comp frame to one HR pixel.  v/a: partial sums per tap parity relative to the centre tap
+// (row parity, col parity) -> the CFA channel of each partial is resolved once at the end.
+template <bool ISO>
+__device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom &g, double lr_x, double lr_y,
+                                            float (&val)[3], float (&acc)[3]) {
+    const int px = (int)floor(lr_x / g.ts), py = (int)floor(lr_y / g.ts);       // merge.py:322-323
+    const float2 fl = __ldg(reinterpret_cast<const float2 *>(f.flow) + py * g.nx + px);
+    const int i_r = min((int)lr_y, g.H - 1), j_r = min((int)lr_x, g.W - 1);     // merge.py:335-336
+    const float local_r = __ldg(f.r + (size_t)i_r * g.W + j_r);
+    const double mx = lr_x + (double)fl.x, my = lr_y + (double)fl.y;             // merge.py:339-340
+    if (!(mx >= 0.0 && mx < (double)g.W && my >= 0.0 && my < (double)g.H)) return;   // :343-345
+    const int cj = (int)mx, ci = (int)my;
+    const float tx = (float)(mx - (double)cj), ty = (float)(my - (double)ci);
+    // quadratic form pre-scaled by -0.5*log2(e): w = exp(-z/2) = 2^(qxx dx^2 + 2 qxy dx dy + qyy dy^2)
+    const float kS = -0.72134752044448170368f;
+    float qxx, qxy, qyy;
+    if (ISO) {
+        qxx = qyy = 2.0f * kS;   // z = 2 (dx^2 + dy^2), merge.py:419
+        qxy = 0.0f;
+    } else {
+        const double kj = mx * 0.5 - 0.5, ki = my * 0.5 - 0.5;                   // merge.py:350-351 (bayer)
+        const double tkj = trunc(kj), tki = trunc(ki);
+        const float frx = (float)(kj - tkj), fry = (float)(ki - tki);           // signed modf, :357-358
+        const int fx0 = max((int)tkj, 0), fy0 = max((int)tki, 0);
+        const int cx1 = min(fx0 + 1, g.cw - 1), cy1 = min(fy0 + 1, g.ch - 1);
+        const float4 *c4 = reinterpret_cast<const float4 *>(f.covs);
+        const float4 tr = __ldg(c4 + (size_t)fy0 * g.cw + fx0), tl = __ldg(c4 + (size_t)fy0 * g.cw + cx1);
+        const float4 br = __ldg(c4 + (size_t)cy1 * g.cw + fx0), bl = __ldg(c4 + (size_t)cy1 * g.cw + cx1);
+        const float top_xx = tr.x + frx * (tl.x - tr.x), bot_xx = br.x + frx * (bl.x - br.x);
+        const float top_xy = tr.y + frx * (tl.y - tr.y), bot_xy = br.y + frx * (bl.y - br.y);
+        const float top_yy = tr.w + frx * (tl.w - tr.w), bot_yy = br.w + frx * (bl.w - br.w);
+        const float cxx = top_xx + fry * (bot_xx - top_xx);
+        const float cxy = top_xy + fry * (bot_xy - top_xy);
+        const float cyy = top_yy + fry * (bot_yy - top_yy);
+        const float inv_det = kS / (cxx * cyy - cxy * cxy);                      // merge.py:391-396
+        qxx = inv_det * cyy;
+        qxy = -2.0f * inv_det * cxy;
+        qyy = inv_det * cxx;
+    }
+    float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, a[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+    for (int di = -1; di <= 1; ++di) {
+        const int i = ci + di;
+        if (i < 0 || i >= g.H) continue;
+        const float dy = (float)di + 0.5f - ty;                                   // i - (lr_mov_y - 0.5)
+        const float *row = f.raw + (size_t)i * g.W;
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) {
+            const int j = cj + dj;
+            if (j < 0 || j >= g.W) continue;
+            const float c = __ldg(row + j);
+            const float dx = (float)dj + 0.5f - tx;
+            float z = qxx * dx * dx + qxy * dx * dy + qyy * dy * dy;
+            z = fminf(0.0f, z);               // == -0.5*log2e*max(0, z_ref); NaN -> 0
+            const float wr = exp2f(z) * local_r;
+            v[di & 1][dj & 1] += wr * c;
+            a[di & 1][dj & 1] += wr;
+        }
+    }
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+        for (int rx = 0; rx < 2; ++rx) {
+            const int chn = cfa_channel(g.cfa, ci + ry, cj + rx);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                val[k] += (chn == k) ? v[ry][rx] : 0.0f;
+                acc[k] += (chn == k) ? a[ry][rx] : 0.0f;
+            }
+        }
+}
+
+template <bool ISO, int VEC>
+__global__ void __launch_bounds__(256) accumulate_kernel(MergeBatch b, MergeGeom g, float *__restrict__ num,
+                                                         float *__restrict__ den) {
+    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (hr_i >= g.Hs || j0 >= g.Ws) return;
+    const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
+    const bool full = (VEC == 4) && (j0 + VEC <= g.Ws);
+    float n[VEC * 3], d[VEC * 3];
+    if (full) {   // 3 x float4 per accumulator, issued before the gathers so HBM latency overlaps the math
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float4 a = *reinterpret_cast<const float4 *>(num + base + 4 * q);
+            const float4 c = *reinterpret_cast<const float4 *>(den + base + 4 * q);
+            n[4 * q] = a.x, n[4 * q + 1] = a.y, n[4 * q + 2] = a.z, n[4 * q + 3] = a.w;
+            d[4 * q] = c.x, d[4 * q + 1] = c.y, d[4 * q + 2] = c.z, d[4 * q + 3] = c.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < VEC * 3; ++q) {
+            const bool ok = j0 + q / 3 < g.Ws;
+            n[q] = ok ? num[base + q] : 0.f;
+            d[q] = ok ? den[base + q] : 0.f;
+        }
+    }
+    const double lr_y = ((double)hr_i + 0.5) / g.scale;                         // merge.py:319-320
+    for (int k = 0; k < b.K; ++k) {
+#pragma unroll
+        for (int p = 0; p < VEC; ++p) {
+            if (j0 + p >= g.Ws) break;
+            float val[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
+            const double lr_x = ((double)(j0 + p) + 0.5) / g.scale;
+            merge_pixel<ISO>(b.f[k], g, lr_x, lr_y, val, acc);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                n[p * 3 + c] += val[c];
+                d[p * 3 + c] += acc[c];
+            }
+        }
+    }
+    if (full) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            *reinterpret_cast<float4 *>(num + base + 4 * q) = make_float4(n[4 * q], n[4 * q + 1], n[4 * q + 2], n[4 * q + 3]);
+            *reinterpret_cast<float4 *>(den + base + 4 * q) = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < VEC * 3; ++q)
+            if (j0 + q / 3 < g.Ws) {
+                num[base + q] = n[q];
+                den[base + q] = d[q];
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Reference frame (merge.py:82-233).  Once per burst: keeps the reference's float64 arithmetic.
+// ---------------------------------------------------------------------------------------------------------
+template <bool ISO>
+__global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__restrict__ raw, const float *__restrict__ covs,
+                                                             MergeGeom g, float *__restrict__ num, float *__restrict__ den,
+                                                             const double *__restrict__ acc_rob, int max_frame_count,
+                                                             int rad_max, double max_multiplier, int fuse_divide) {
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox >= g.Ws || oy >= g.Hs) return;
+    const float pos_y = (float)((double)oy / g.scale), pos_x = (float)((double)ox / g.scale);   // :113-114
+    float i00 = 1.f, i01 = 0.f, i10 = 0.f, i11 = 1.f;
+    if (!ISO) {
+        const float gy = (float)(((double)pos_y - 0.5) / 2.0), gx = (float)(((double)pos_x - 0.5) / 2.0);
+        const int fx0 = (int)fmaxf(floorf(gx), 0.f), fy0 = (int)fmaxf(floorf(gy), 0.f);
+        const int cx1 = min(fx0 + 1, g.cw - 1), cy1 = min(fy0 + 1, g.ch - 1);
+        const double rx = (double)(gx - truncf(gx)), ry = (double)(gy - truncf(gy));            // linalg.py:190-191
+        const float4 *c4 = reinterpret_cast<const float4 *>(covs);
+        const float4 c00 = __ldg(c4 + (size_t)fy0 * g.cw + fx0), c01 = __ldg(c4 + (size_t)fy0 * g.cw + cx1);
+        const float4 c10 = __ldg(c4 + (size_t)cy1 * g.cw + fx0), c11 = __ldg(c4 + (size_t)cy1 * g.cw + cx1);
+        const double w00 = (1 - rx) * (1 - ry), w01 = rx * (1 - ry), w10 = (1 - rx) * ry, w11 = rx * ry;
+        // linalg.py:194-199: ((a*(1-rx))*(1-ry) + ...) evaluated left to right in float64, stored float32
+        auto mix = [&](float a, float b, float c, float d) {
+            return (float)((double)a * (1 - rx) * (1 - ry) + (double)b * rx * (1 - ry) + (double)c * (1 - rx) * ry +
+                           (double)d * rx * ry);
+        };
+        (void)w00, (void)w01, (void)w10, (void)w11;
+        const float m00 = mix(c00.x, c01.x, c10.x, c11.x), m01 = mix(c00.y, c01.y, c10.y, c11.y);
+        const float m10 = mix(c00.z, c01.z, c10.z, c11.z), m11 = mix(c00.w, c01.w, c10.w, c11.w);
+        const float det = m00 * m11 - m01 * m10;                                                 // linalg.py:53
+        if (fabs((double)det) > 1e-10) {
+            const double det_i = 1.0 / (double)det;
+            i00 = (float)((double)m11 * det_i);
+            i01 = (float)((double)(-m01) * det_i);
+            i10 = (float)((double)(-m10) * det_i);
+            i11 = (float)((double)m00 * det_i);
+        }
+    }
+    double power = 1.0;
+    int rad = 1;
+    bool overwrite = false;
+    if (acc_rob != nullptr) {                                                                    // :167-176
+        const int ay = min((int)llrint((double)pos_y), g.H - 1), ax = min((int)llrint((double)pos_x), g.W - 1);
+        const double la = acc_rob[(size_t)ay * g.W + ax];
+        if (la <= (double)max_frame_count) {
+            power = max_multiplier;
+            rad = rad_max;
+        }
+        overwrite = la < (double)max_frame_count;
+    }
+    const int cx = (int)llrint((double)pos_x), cy = (int)llrint((double)pos_y);                  // round half even
+    float val[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
+    for (int i = -rad; i <= rad; ++i) {
+        const int yy = cy + i;
+        if (yy < 0 || yy >= g.H) continue;
+        for (int j = -rad; j <= rad; ++j) {
+            const int xx = cx + j;
+            if (xx < 0 || xx >= g.W) continue;
+            const int chn = cfa_channel(g.cfa, yy, xx);
+            const double c = (double)__ldg(raw + (size_t)yy * g.W + xx);
+            const double dx = (double)xx - (double)pos_x, dy = (double)yy - (double)pos_y;
+            double y;
+            if (ISO)
+                y = 2 * (dx * dx + dy * dy);
+            else
+                y = (double)i00 * dx * dx + dx * dy * (double)(i01 + i10) + (double)i11 * dy * dy;  // linalg.py:83
+            y = (y > 0) ? y : 0.0;
+            y /= power;
+            const double w = exp(-0.5 * y);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (chn == k) {
+                    val[k] = (float)((double)val[k] + c * w);
+                    acc[k] = (float)((double)acc[k] + w);
+                }
+        }
+    }
+    const size_t o = ((size_t)oy * g.Ws + ox) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float nn = overwrite ? val[k] : num[o + k] + val[k];
+        const float dd = overwrite ? acc[k] : den[o + k] + acc[k];
+        if (fuse_divide) nn = nn / dd;
+        num[o + k] = nn;
+        den[o + k] = dd;
+    }
+}
+
+__global__ void divide_kernel(float *__restrict__ num, const float *__restrict__ den, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            float4 a = *reinterpret_cast<float4 *>(num + i);
+            const float4 b = *reinterpret_cast<const float4 *>(den + i);
+            a.x /= b.x, a.y /= b.y, a.z /= b.z, a.w /= b.w;
+            *reinterpret_cast<float4 *>(num + i) = a;
+        } else {
+            for (size_t k = i; k < n; ++k) num[k] /= den[k];
+        }
+    }
+}
+
+__global__ void add_f64_f32_kernel(double *__restrict__ A, const float *__restrict__ B, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) A[i] += (double)B[i];
+}
+
+static int check_merge_args(const void *raw, const void *num, const void *den, int H, int W, int Hs, int Ws,
+                            double scale, const int *cfa) {
+    HHSR_REQUIRE(raw && num && den && cfa, "null pointer");
+    HHSR_REQUIRE(H > 1 && W > 1 && Hs > 0 && Ws > 0, "non-positive size");
+    HHSR_REQUIRE(scale >= 1.0, "scale must be >= 1 (params.py:8)");
+    HHSR_REQUIRE(((uintptr_t)num % 16 == 0) && ((uintptr_t)den % 16 == 0), "num/den must be 16-byte aligned");
+    return 0;
+}
+
+static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso,
+                             cudaStream_t st) {
+    const bool vec = (g.Ws % 4 == 0);
+    dim3 block(32, 8);
+    if (vec) {
+        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8));
+        if (iso)
+            accumulate_kernel<true, 4><<<grid, block, 0, st>>>(b, g, num, den);
+        else
+            accumulate_kernel<false, 4><<<grid, block, 0, st>>>(b, g, num, den);
+    } else {
+        dim3 grid(ceil_div(g.Ws, 32), ceil_div(g.Hs, 8));
+        if (iso)
+            accumulate_kernel<true, 1><<<grid, block, 0, st>>>(b, g, num, den);
+        else
+            accumulate_kernel<false, 1><<<grid, block, 0, st>>>(b, g, num, den);
+    }
+    return launch_status("merge_accumulate");
+}
+
+}  // namespace hhsr
+
+using namespace hhsr;
+
+extern "C" int hhsr_merge_accumulate_batch(const float *const *raws, const float *const *flows,
+                                           const float *const *covs, const float *const *rs, int K, int H, int W,
+                                           int ny, int nx, int ts, float *num, float *den, int Hs, int Ws,
+                                           double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
+    HHSR_REQUIRE(raws && flows && rs && K > 0, "null frame list");
+    HHSR_REQUIRE(iso || covs, "covs required for the steerable kernel");
+    if (int e = check_merge_args(raws[0], num, den, H, W, Hs, Ws, scale, cfa_host)) return e;
+    HHSR_REQUIRE(ts > 0 && ny * ts >= H && nx * ts >= W, "flow grid does not cover the frame");
+    MergeGeom g{H, W, nx, ts, H / 2, W / 2, Hs, Ws, pack_cfa(cfa_host), scale};
+    for (int k0 = 0; k0 < K; k0 += kMaxBatch) {
+        MergeBatch b;
+        b.K = (K - k0 < kMaxBatch) ? K - k0 : kMaxBatch;
+        for (int k = 0; k < b.K; ++k) {
+            HHSR_REQUIRE(raws[k0 + k] && flows[k0 + k] && rs[k0 + k], "null frame pointer");
+            HHSR_REQUIRE(iso || ((uintptr_t)covs[k0 + k] % 16 == 0 && covs[k0 + k]), "covs must be 16-byte aligned");
+            b.f[k] = MergeFrame{raws[k0 + k], flows[k0 + k], iso ? nullptr : covs[k0 + k], rs[k0 + k]};
+        }
+        if (int e = launch_accumulate(b, g, num, den, iso, (cudaStream_t)stream)) return e;
+    }
+    return 0;
+}
+
+extern "C" int hhsr_merge_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
+                                     const float *covs, const float *r, float *num, float *den, int Hs, int Ws,
+                                     double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
+    return hhsr_merge_accumulate_batch(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale,
+                                       cfa_host, iso, stream);
+}
+
+extern "C" int hhsr_merge_ref(const float *raw, int H, int W, const float *covs, float *num, float *den, int Hs,
+                              int Ws, double scale, const int *cfa_host, int iso, const double *acc_rob,
+                              int max_frame_count, int rad_max, double max_multiplier, int fuse_divide,
+                              hhsr_stream_t stream) {
+    if (int e = check_merge_args(raw, num, den, H, W, Hs, Ws, scale, cfa_host)) return e;
+    HHSR_REQUIRE(iso || (covs && (uintptr_t)covs % 16 == 0), "covs required (16-byte aligned) for the steerable kernel");
+    HHSR_REQUIRE(acc_rob == nullptr || rad_max >= 0, "rad_max must be >= 0");
+    MergeGeom g{H, W, 0, 0, H / 2, W / 2, Hs, Ws, pack_cfa(cfa_host), scale};
+    dim3 block(32, 8), grid(ceil_div(Ws, 32), ceil_div(Hs, 8));
+    if (iso)
+        accumulate_ref_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(raw, covs, g, num, den, acc_rob, max_frame_count,
+                                                                             rad_max, max_multiplier, fuse_divide);
+    else
+        accumulate_ref_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(raw, covs, g, num, den, acc_rob, max_frame_count,
+                                                                              rad_max, max_multiplier, fuse_divide);
+    return launch_status("merge_ref");
+}
+
+extern "C" int hhsr_divide(float *num, const float *den, size_t n, hhsr_stream_t stream) {
+    HHSR_REQUIRE(num && den && n > 0, "null pointer or empty array");
+    HHSR_REQUIRE(((uintptr_t)num % 16 == 0) && ((uintptr_t)den % 16 == 0), "num/den must be 16-byte aligned");
+    const int block = 256;
+    size_t blocks = (n / 4 + block - 1) / block + 1;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    divide_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(num, den, n);
+    return launch_status("divide");
+}
+
+extern "C" int hhsr_add_f64_f32(double *A, const float *B, size_t n, hhsr_stream_t stream) {
+    HHSR_REQUIRE(A && B && n > 0, "null pointer or empty array");
+    const int block = 256;
+    size_t blocks = (n + block - 1) / block;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    add_f64_f32_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(A, B, n);
+    return launch_status("add");
+}

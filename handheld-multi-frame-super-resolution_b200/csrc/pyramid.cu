@@ -1,0 +1,128 @@
+// Grey-image band mask and Gaussian pyramid for sm_100a.
+//
+// Replaces handheld_super_resolution/utils_image.py:82-100 (the four masked fills + two fftshift copies of
+// compute_grey_images; the FFTs themselves stay cuFFT), alignment.py:26-37 (circular padding) and
+// utils_image.py:360-391 (cuda_downsample: two full-resolution F.conv2d followed by a strided slice).  The
+// downsample kernel computes only the kept outputs: y pass then x pass inside one CTA, input tile staged in
+// shared memory, so HBM traffic is one read of the level plus one write of the next (the reference reads and
+// writes the full-resolution image three times).
+#include "common.cuh"
+
+namespace hhsr {
+
+// keep flag of the reference's mask on the UNSHIFTED frequency index k of an axis of length n:
+// shifted index s = (k + n/2) mod n is kept iff n/4 <= s < n - ceil(n/4)   (utils_image.py:92-95)
+__device__ __forceinline__ bool band_keep(int k, int n) {
+    const int s = (k + n / 2) % n;
+    return s >= n / 4 && s < n - (n + 3) / 4;
+}
+
+// sy/sx: strides of spec in complex elements.  torch.fft.rfft2 on CUDA returns a column-major [H][W/2+1] tensor
+// (strides (1, H)); xfast selects which index runs along threadIdx.x so that accesses stay coalesced either way.
+__global__ void grey_band_mask_kernel(float2 *__restrict__ spec, int H, int W, int Wc, long long sy, long long sx,
+                                      int xfast) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+    const int kx = xfast ? f : s, ky = xfast ? s : f;
+    if (kx >= Wc || ky >= H) return;
+    const float a = (band_keep(ky, H) && band_keep(kx, W)) ? 0.5f : 0.f;
+    const float b = (band_keep((H - ky) % H, H) && band_keep((W - kx) % W, W)) ? 0.5f : 0.f;
+    const float m = a + b;   // Re(ifft2(M F)) == ifft2(0.5 (M(k) + M(-k)) F) for a real image
+    float2 *p = spec + (long long)ky * sy + (long long)kx * sx;
+    if (m == 0.f)
+        *p = make_float2(0.f, 0.f);
+    else if (m != 1.f) {
+        float2 v = *p;
+        v.x *= m, v.y *= m;
+        *p = v;
+    }
+}
+
+__global__ void pad_circular_kernel(const float *__restrict__ src, int h, int w, float *__restrict__ dst, int hp, int wp) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= wp || y >= hp) return;
+    dst[(size_t)y * wp + x] = __ldg(src + (size_t)(y % h) * w + (x % w));
+}
+
+constexpr int kMaxTaps = 33;
+struct Taps {
+    float g[kMaxTaps];
+};
+constexpr int DBX = 32, DBY = 8;
+
+// dynamic smem: in[(DBY*f + 2R)][(DBX*f + 2R)] then tmp[DBY][(DBX*f + 2R)]
+__global__ void __launch_bounds__(DBX *DBY) gauss_downsample_kernel(const float *__restrict__ src, int h, int w, int f, int R,
+                                                                    Taps taps, float *__restrict__ dst, int h2, int w2) {
+    extern __shared__ float sm[];
+    const int K = 2 * R + 1;
+    const int tin_w = DBX * f + 2 * R, tin_h = DBY * f + 2 * R;
+    float *tin = sm, *tmp = sm + tin_w * tin_h;
+    const int ox0 = blockIdx.x * DBX, oy0 = blockIdx.y * DBY;
+    const int ix0 = ox0 * f, iy0 = oy0 * f;
+    const int tid = threadIdx.y * DBX + threadIdx.x;
+    for (int t = tid; t < tin_w * tin_h; t += DBX * DBY) {
+        const int ly = t / tin_w, lx = t % tin_w;
+        const int gy = iy0 + ly, gx = ix0 + lx;
+        tin[t] = (gy < h && gx < w) ? __ldg(src + (size_t)gy * w + gx) : 0.f;
+    }
+    __syncthreads();
+    // y pass (first F.conv2d, utils_image.py:383): only the DBY kept rows
+    for (int t = tid; t < DBY * tin_w; t += DBX * DBY) {
+        const int r = t / tin_w, c = t % tin_w;
+        float acc = 0.f;
+        for (int a = 0; a < K; ++a) acc = fmaf(taps.g[a], tin[(r * f + a) * tin_w + c], acc);
+        tmp[t] = acc;
+    }
+    __syncthreads();
+    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
+    if (ox >= w2 || oy >= h2) return;
+    float acc = 0.f;   // x pass (second F.conv2d, :384)
+    for (int b = 0; b < K; ++b) acc = fmaf(taps.g[b], tmp[threadIdx.y * tin_w + threadIdx.x * f + b], acc);
+    dst[(size_t)oy * w2 + ox] = acc;
+}
+
+}  // namespace hhsr
+
+using namespace hhsr;
+
+extern "C" int hhsr_grey_band_mask(float *spec, int H, int W, long long stride_y, long long stride_x,
+                                   hhsr_stream_t stream) {
+    HHSR_REQUIRE(spec, "null pointer");
+    HHSR_REQUIRE(H > 0 && W > 0, "non-positive size");
+    HHSR_REQUIRE((uintptr_t)spec % 8 == 0, "spectrum must be 8-byte aligned");
+    HHSR_REQUIRE(stride_y > 0 && stride_x > 0, "strides must be positive");
+    const int Wc = W / 2 + 1;
+    const int xfast = stride_x <= stride_y;
+    const int nfast = xfast ? Wc : H, nslow = xfast ? H : Wc;
+    dim3 block(128), grid(ceil_div(nfast, 128), nslow);
+    grey_band_mask_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2 *>(spec), H, W, Wc, stride_y,
+                                                                   stride_x, xfast);
+    return launch_status("grey_band_mask");
+}
+
+extern "C" int hhsr_pad_circular(const float *src, int h, int w, float *dst, int hp, int wp, hhsr_stream_t stream) {
+    HHSR_REQUIRE(src && dst, "null pointer");
+    HHSR_REQUIRE(h > 0 && w > 0 && hp >= h && wp >= w, "padded size must be >= source size");
+    dim3 block(32, 8), grid(ceil_div(wp, 32), ceil_div(hp, 8));
+    pad_circular_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, h, w, dst, hp, wp);
+    return launch_status("pad_circular");
+}
+
+extern "C" int hhsr_gauss_downsample(const float *src, int h, int w, int factor, const float *taps_host, int radius,
+                                     float *dst, int h2, int w2, hhsr_stream_t stream) {
+    HHSR_REQUIRE(src && dst && taps_host, "null pointer");
+    HHSR_REQUIRE(factor >= 1 && radius >= 0 && 2 * radius + 1 <= kMaxTaps, "factor/radius out of range");
+    HHSR_REQUIRE(h > 2 * radius && w > 2 * radius, "level smaller than the filter");
+    HHSR_REQUIRE(h2 == (h - 2 * radius) / factor && w2 == (w - 2 * radius) / factor && h2 > 0 && w2 > 0,
+                 "output shape must be ((h-2r)/f, (w-2r)/f)");
+    Taps t;
+    for (int i = 0; i < 2 * radius + 1; ++i) t.g[i] = taps_host[i];
+    const int tin_w = DBX * factor + 2 * radius, tin_h = DBY * factor + 2 * radius;
+    const size_t smem = (size_t)(tin_w * tin_h + DBY * tin_w) * sizeof(float);
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return unsupported("downsampling factor too large for one CTA tile");
+        cudaFuncSetAttribute(gauss_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    dim3 block(DBX, DBY), grid(ceil_div(w2, DBX), ceil_div(h2, DBY));
+    gauss_downsample_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(src, h, w, factor, radius, t, dst, h2, w2);
+    return launch_status("gauss_downsample");
+}

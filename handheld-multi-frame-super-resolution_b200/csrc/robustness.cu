@@ -1,0 +1,263 @@
+// Robustness estimation (Alg. 6-9) for sm_100a.
+//
+// Replaces handheld_super_resolution/robustness.py: cuda_compute_guide_image (:206-226) + cuda_compute_local_stats
+// (:268-294) -> guide_stats_kernel; cuda_uspcale_dogson (:358-418) -> upscale_warp_kernel; and the chain
+// upscale_warp(comp) -> cuda_compute_dist (:452-462) -> cuda_apply_noise_model (:504-533) -> cuda_compute_s
+// (:569-611) -> cuda_robustness_threshold (:626-639) -> robustness_kernel (one pass, no full-size temporaries;
+// the reference materialises 9 of them); cuda_compute_local_min (:669-687) + utils.cuda_add (:116-120) ->
+// local_min5_kernel.
+//
+// Arithmetic follows the compiled reference: float64 wherever Numba promotes (white-balance division, Dodgson
+// weights, noise-model shrinkage, the final S*exp - t), float32 sums where the reference keeps float32 arrays.
+#include "common.cuh"
+
+namespace hhsr {
+
+constexpr int RBX = 32, RBY = 8;
+
+struct GuideParams {
+    int cfa;         // packed 2x2 channel ids
+    double wb[3];
+};
+
+// guide value of channel c at guide pixel (y, x): robustness.py:206-226
+__device__ __forceinline__ void guide_rgb(const float *__restrict__ raw, int W, int y, int x, const GuideParams &p,
+                                          float (&out)[3]) {
+    const float2 a = __ldg(reinterpret_cast<const float2 *>(raw + (size_t)(2 * y) * W + 2 * x));
+    const float2 b = __ldg(reinterpret_cast<const float2 *>(raw + (size_t)(2 * y + 1) * W + 2 * x));
+    const float q[4] = {a.x, a.y, b.x, b.y};
+    double g = 0.0;
+    out[0] = out[1] = out[2] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = (p.cfa >> (2 * k)) & 3;
+        const double v = (double)q[k] / p.wb[c];
+        if (c == 1)
+            g += v;
+        else
+            out[c] = (float)v;
+    }
+    out[1] = (float)(g / 2.0);
+}
+
+__global__ void __launch_bounds__(RBX *RBY) guide_stats_kernel(const float *__restrict__ raw, int W, int h, int w,
+                                                               GuideParams p, float *__restrict__ means,
+                                                               float *__restrict__ vars) {
+    __shared__ float s[3][RBY + 2][RBX + 2];
+    const int x0 = blockIdx.x * RBX, y0 = blockIdx.y * RBY;
+    for (int t = threadIdx.y * RBX + threadIdx.x; t < (RBY + 2) * (RBX + 2); t += RBX * RBY) {
+        const int ly = t / (RBX + 2), lx = t % (RBX + 2);
+        const int gy = min(max(y0 + ly - 1, 0), h - 1), gx = min(max(x0 + lx - 1, 0), w - 1);   // clamp, :287-288
+        float rgb[3];
+        guide_rgb(raw, W, gy, gx, p, rgb);
+        s[0][ly][lx] = rgb[0], s[1][ly][lx] = rgb[1], s[2][ly][lx] = rgb[2];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float v = s[c][threadIdx.y + i][threadIdx.x + j];
+                s1 += v;
+                s2 = __fmaf_rn(v, v, s2);
+            }
+        const double m = (double)s1 / 9.0;
+        const size_t o = ((size_t)c * h + y) * w + x;
+        means[o] = (float)m;
+        if (vars) vars[o] = (float)((double)s2 / 9.0 - m * m);
+    }
+}
+
+__device__ __forceinline__ double dodgson(double t) {   // utils_image.py:398-406
+    const double a = fabs(t);
+    if (a <= 0.5) return -2.0 * a * a + 1.0;
+    if (a <= 1.5) return a * a - 5.0 / 2.0 * a + 1.5;
+    return 0.0;
+}
+
+// x2 Dodgson upsampling of a 3-channel statistic at raw pixel (y, x) displaced by (fx, fy); false if the source
+// position leaves the guide image (the reference then writes +inf).
+__device__ __forceinline__ bool dodgson_sample(const float *__restrict__ lr, int h, int w, int y, int x, float fx,
+                                               float fy, float (&out)[3]) {
+    const double ly = ((double)y + (double)fy + 0.5) / 2.0 - 0.5;    // robustness.py:380-381 (s = 2)
+    const double lx = ((double)x + (double)fx + 0.5) / 2.0 - 0.5;
+    if (!(0.0 <= ly && ly < (double)h && 0.0 <= lx && lx < (double)w)) return false;
+    const int cy = (int)llrint(ly), cx = (int)llrint(lx);
+    float buf[3] = {0.f, 0.f, 0.f};
+    double wacc = 0.0;
+    const size_t plane = (size_t)h * w;
+#pragma unroll
+    for (int i = -1; i <= 1; ++i) {
+        const int y_ = min(max(cy + i, 0), h - 1);
+        const double wy = dodgson((double)y_ - ly);
+#pragma unroll
+        for (int j = -1; j <= 1; ++j) {
+            const int x_ = min(max(cx + j, 0), w - 1);
+            const double wgt = wy * dodgson((double)x_ - lx);
+            const float *q = lr + (size_t)y_ * w + x_;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) buf[c] = (float)((double)buf[c] + (double)__ldg(q + c * plane) * wgt);
+            wacc += wgt;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = (float)((double)buf[c] / wacc);
+    return true;
+}
+
+__global__ void __launch_bounds__(RBX *RBY) upscale_warp_kernel(const float *__restrict__ lr, int h, int w,
+                                                                const float *__restrict__ flow, int nx, int ts,
+                                                                float *__restrict__ hr) {
+    const int x = blockIdx.x * RBX + threadIdx.x, y = blockIdx.y * RBY + threadIdx.y;
+    const int H = 2 * h, W = 2 * w;
+    if (x >= W || y >= H) return;
+    float fx = 0.f, fy = 0.f;
+    if (flow) {
+        const float2 f = __ldg(reinterpret_cast<const float2 *>(flow) + (size_t)(y / ts) * nx + x / ts);
+        fx = f.x, fy = f.y;
+    }
+    float v[3];
+    const bool ok = dodgson_sample(lr, h, w, y, x, fx, fy, v);
+    const size_t plane = (size_t)H * W, o = (size_t)y * W + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) hr[o + c * plane] = ok ? v[c] : INFINITY;
+}
+
+struct RobParams {
+    double t, s1, s2, Mt;
+    int n_curve;
+};
+
+__global__ void __launch_bounds__(RBX *RBY) robustness_kernel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
+                                                              const float *__restrict__ ref_vars, int H, int W,
+                                                              const float *__restrict__ flow, int ny, int nx, int ts,
+                                                              const double *__restrict__ std_curve,
+                                                              const double *__restrict__ diff_curve, RobParams p,
+                                                              float *__restrict__ R) {
+    const int x = blockIdx.x * RBX + threadIdx.x, y = blockIdx.y * RBY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int py = y / ts, px = x / ts;
+    const float2 *fl = reinterpret_cast<const float2 *>(flow);
+    const float2 f = __ldg(fl + (size_t)py * nx + px);
+    float cm[3];
+    const bool ok = dodgson_sample(comp_lr, H / 2, W / 2, y, x, f.x, f.y, cm);
+    const size_t plane = (size_t)H * W, o = (size_t)y * W + x;
+    float out = 0.f;   // any non-finite statistic ends as clamp(NaN) = 0 in the reference
+    const float rm0 = __ldg(ref_means + o);
+    if (ok && isfinite(rm0)) {
+        double sigma_sq = 0.0, d_sq = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float brightness = c == 0 ? rm0 : __ldg(ref_means + o + c * plane);
+            long long id = llrint(1000.0 * (double)brightness);                 // robustness.py:519
+            id = id < 0 ? 0 : (id >= p.n_curve ? p.n_curve - 1 : id);
+            const double d_t = __ldg(diff_curve + id), sigma_t = __ldg(std_curve + id);
+            const float sigma_p_sq = __ldg(ref_vars + o + c * plane);
+            const double st2 = sigma_t * sigma_t;
+            sigma_sq += (st2 > (double)sigma_p_sq) ? st2 : (double)sigma_p_sq;  // max(sigma_p_sq, sigma_t^2)
+            const float d_p = fabsf(brightness - cm[c]);                        // :462
+            const float d_p_sq = __fmul_rn(d_p, d_p);
+            const double shrink = (double)d_p_sq / ((double)d_p_sq + d_t * d_t);
+            d_sq += (double)d_p_sq * shrink * shrink;
+        }
+        const float sigma_f = (float)sigma_sq, d_f = (float)d_sq;               // stored as float32 arrays
+        // flow irregularity, robustness.py:569-611
+        float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+#pragma unroll
+        for (int i = -1; i <= 1; ++i)
+#pragma unroll
+            for (int j = -1; j <= 1; ++j) {
+                const int yy = py + i, xx = px + j;
+                if (yy < 0 || yy >= ny || xx < 0 || xx >= nx) continue;
+                const float2 q = __ldg(fl + (size_t)yy * nx + xx);
+                mxx = fmaxf(mxx, q.x), mxy = fmaxf(mxy, q.y), mnx = fminf(mnx, q.x), mny = fminf(mny, q.y);
+            }
+        const float d0 = mxx - mnx, d1 = mxy - mny;
+        const float S = ((double)(d0 * d0 + d1 * d1) > p.Mt * p.Mt) ? (float)p.s1 : (float)p.s2;
+        const float e = expf(-d_f / sigma_f);                                    // math.exp(float32), :638
+        double v = (double)(S * e) - p.t;
+        v = (v > 0.0) ? v : 0.0;
+        v = (v < 1.0) ? v : 1.0;
+        out = (float)v;
+    }
+    R[o] = out;
+}
+
+__global__ void __launch_bounds__(RBX *RBY) local_min5_kernel(const float *__restrict__ R, int H, int W, float *__restrict__ r,
+                                                              double *__restrict__ acc_rob) {
+    __shared__ float s[RBY + 4][RBX + 4];
+    const int x0 = blockIdx.x * RBX, y0 = blockIdx.y * RBY;
+    for (int t = threadIdx.y * RBX + threadIdx.x; t < (RBY + 4) * (RBX + 4); t += RBX * RBY) {
+        const int ly = t / (RBX + 4), lx = t % (RBX + 4);
+        const int gy = min(max(y0 + ly - 2, 0), H - 1), gx = min(max(x0 + lx - 2, 0), W - 1);
+        s[ly][lx] = __ldg(R + (size_t)gy * W + gx);
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float m = INFINITY;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) m = fminf(m, s[threadIdx.y + i][threadIdx.x + j]);
+    const size_t o = (size_t)y * W + x;
+    r[o] = m;
+    if (acc_rob) acc_rob[o] += (double)m;
+}
+
+}  // namespace hhsr
+
+using namespace hhsr;
+
+extern "C" int hhsr_guide_stats(const float *raw, int H, int W, const int *cfa_host, const double *wb_host,
+                                float *means, float *vars, hhsr_stream_t stream) {
+    HHSR_REQUIRE(raw && cfa_host && wb_host && means, "null pointer");
+    HHSR_REQUIRE(H >= 2 && W >= 2 && W % 2 == 0, "frame must be at least 2x2 with an even width");
+    HHSR_REQUIRE((uintptr_t)raw % 8 == 0, "raw must be 8-byte aligned");
+    GuideParams p;
+    p.cfa = pack_cfa(cfa_host);
+    for (int k = 0; k < 4; ++k) HHSR_REQUIRE(cfa_host[k] >= 0 && cfa_host[k] <= 2, "cfa entries must be 0, 1 or 2");
+    for (int c = 0; c < 3; ++c) p.wb[c] = wb_host[c];
+    const int h = H / 2, w = W / 2;
+    dim3 block(RBX, RBY), grid(ceil_div(w, RBX), ceil_div(h, RBY));
+    guide_stats_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(raw, W, h, w, p, means, vars);
+    return launch_status("guide_stats");
+}
+
+extern "C" int hhsr_upscale_warp_stats(const float *lr, int h, int w, const float *flow, int ny, int nx, int ts,
+                                       float *hr, hhsr_stream_t stream) {
+    HHSR_REQUIRE(lr && hr, "null pointer");
+    HHSR_REQUIRE(h > 0 && w > 0, "non-positive size");
+    HHSR_REQUIRE(flow == nullptr || (ts > 0 && ny * ts >= 2 * h && nx * ts >= 2 * w), "flow grid does not cover the frame");
+    dim3 block(RBX, RBY), grid(ceil_div(2 * w, RBX), ceil_div(2 * h, RBY));
+    upscale_warp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(lr, h, w, flow, nx, ts > 0 ? ts : 1, hr);
+    return launch_status("upscale_warp_stats");
+}
+
+extern "C" int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_vars, int H,
+                               int W, const float *flow, int ny, int nx, int ts, const double *std_curve,
+                               const double *diff_curve, int n_curve, double t, double s1, double s2, double Mt,
+                               float *R, hhsr_stream_t stream) {
+    HHSR_REQUIRE(comp_means_lr && ref_means && ref_vars && flow && std_curve && diff_curve && R, "null pointer");
+    HHSR_REQUIRE(H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "frame sides must be even");
+    HHSR_REQUIRE(ts > 0 && ny * ts >= H && nx * ts >= W, "flow grid does not cover the frame");
+    HHSR_REQUIRE(n_curve > 0, "empty noise curves");
+    RobParams p{t, s1, s2, Mt, n_curve};
+    dim3 block(RBX, RBY), grid(ceil_div(W, RBX), ceil_div(H, RBY));
+    robustness_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(comp_means_lr, ref_means, ref_vars, H, W, flow, ny, nx, ts,
+                                                               std_curve, diff_curve, p, R);
+    return launch_status("robustness");
+}
+
+extern "C" int hhsr_local_min5(const float *R, int H, int W, float *r, double *acc_rob, hhsr_stream_t stream) {
+    HHSR_REQUIRE(R && r, "null pointer");
+    HHSR_REQUIRE(H > 0 && W > 0, "non-positive size");
+    dim3 block(RBX, RBY), grid(ceil_div(W, RBX), ceil_div(H, RBY));
+    local_min5_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(R, H, W, r, acc_rob);
+    return launch_status("local_min5");
+}

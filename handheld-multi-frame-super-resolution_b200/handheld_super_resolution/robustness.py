@@ -1,0 +1,78 @@
+"""Robustness estimation (Alg. 6-9) — mirrors handheld_super_resolution/robustness.py of the reference
+(init_robustness :23-76, compute_robustness :79-170 and the sub-stages it exposes)."""
+import torch
+
+from . import _lib
+
+
+def compute_guide_stats(raw_img, cfa_pattern, white_balance, need_vars=True):
+    """Guide image (Alg. 7, robustness.py:173-226) fused with its 3x3 local statistics (Alg. 8, :228-294).
+    Returns (means, vars) [3, H//2, W//2]; vars is None when not requested."""
+    raw_img = _lib.as_device(raw_img)
+    H, W = raw_img.shape
+    means = torch.empty((3, H // 2, W // 2), dtype=torch.float32, device=raw_img.device)
+    vars_ = torch.empty_like(means) if need_vars else None
+    _lib.call("hhsr_guide_stats", _lib.ptr(raw_img), H, W, _lib.cfa_array(cfa_pattern), _lib.wb_array(white_balance),
+              _lib.ptr(means), _lib.ptr(vars_), _lib.stream())
+    return means, vars_
+
+
+def upscale_warp_stats(local_stats, tile_size=None, flow=None):
+    """x2 Dodgson upsampling (+ warp by the tile flow) of a [3,h,w] statistic to [3,2h,2w] (robustness.py:296-418)."""
+    local_stats = _lib.as_device(local_stats)
+    c, h, w = local_stats.shape
+    if c != 3:
+        raise ValueError("Incoherent number of channel : {}".format(c))
+    out = torch.empty((3, 2 * h, 2 * w), dtype=torch.float32, device=local_stats.device)
+    if flow is None:
+        _lib.call("hhsr_upscale_warp_stats", _lib.ptr(local_stats), h, w, None, 0, 0, 0, _lib.ptr(out), _lib.stream())
+    else:
+        flow = _lib.as_device(flow)
+        _lib.call("hhsr_upscale_warp_stats", _lib.ptr(local_stats), h, w, _lib.ptr(flow), flow.shape[0], flow.shape[1],
+                  int(tile_size), _lib.ptr(out), _lib.stream())
+    return out
+
+
+def init_robustness(ref_img, cfa_pattern, white_balance, config):
+    """Local statistics of the reference frame, upsampled to raw resolution (robustness.py:23-76).
+    Returns (local_means, local_stds) [3, H, W] — `local_stds` holds variances, like the reference."""
+    if not config.robustness.enabled:
+        return None, None
+    if config.mode != "bayer":
+        raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
+    means, vars_ = compute_guide_stats(ref_img, cfa_pattern, white_balance)
+    return upscale_warp_stats(means), upscale_warp_stats(vars_)
+
+
+def local_min(R, acc_rob=None):
+    """5x5 local minimum (Alg. 9, robustness.py:641-687); optionally fused with `acc_rob += r` (utils.add)."""
+    R = _lib.as_device(R)
+    r = torch.empty_like(R)
+    _lib.call("hhsr_local_min5", _lib.ptr(R), R.shape[0], R.shape[1], _lib.ptr(r), _lib.ptr(acc_rob), _lib.stream())
+    return r
+
+
+def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pattern, white_balance, noise_model,
+                       config, acc_rob=None, return_R=False):
+    """Robustness map r [H, W] of comp frame J_n (Alg. 6, robustness.py:79-170).  Three launches: guide statistics
+    at half resolution, the fused per-pixel kernel (warp, distance, noise model, S, threshold), 5x5 minimum.
+    `acc_rob` (float64 [H,W]), when given, is incremented by r in the last launch (super_resolution.py:159)."""
+    comp_img = _lib.as_device(comp_img)
+    H, W = comp_img.shape
+    if not config.robustness.enabled:
+        return torch.ones((H, W), dtype=torch.float32, device=comp_img.device)
+    if config.mode != "bayer":
+        raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
+    tun = config.robustness.tuning
+    ts = config.block_matching.tuning.tile_size
+    std_curve, diff_curve = noise_model
+    std_curve = _lib.as_device(std_curve, torch.float64)
+    diff_curve = _lib.as_device(diff_curve, torch.float64)
+    flows = _lib.as_device(flows)
+    comp_means, _ = compute_guide_stats(comp_img, cfa_pattern, white_balance, need_vars=False)
+    R = torch.empty((H, W), dtype=torch.float32, device=comp_img.device)
+    _lib.call("hhsr_robustness", _lib.ptr(comp_means), _lib.ptr(ref_local_means), _lib.ptr(ref_local_stds), H, W,
+              _lib.ptr(flows), flows.shape[0], flows.shape[1], int(ts), _lib.ptr(std_curve), _lib.ptr(diff_curve),
+              std_curve.numel(), float(tun.t), float(tun.s1), float(tun.s2), float(tun.Mt), _lib.ptr(R), _lib.stream())
+    r = local_min(R, acc_rob)
+    return (r, R) if return_R else r

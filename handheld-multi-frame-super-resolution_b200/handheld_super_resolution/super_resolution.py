@@ -1,0 +1,171 @@
+"""Alg. 1 (HandheldBurstSuperResolution) — mirrors handheld_super_resolution/super_resolution.py of the reference:
+main (:41-200) is the device pipeline, process (:203-360) the host wrapper around it."""
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .alignment import align, init_alignment
+from .kernels import estimate_kernels
+from .merge import merge, merge_batch, merge_ref
+from .params import sanitize_config, update_snr_config
+from .robustness import compute_robustness, init_robustness
+from .utils import divide, timer
+from .utils_image import compute_grey_images
+
+
+def _upload(frame, stream_ready=None):
+    """Host frame -> device (pinned staging handled by the caller for the async path)."""
+    if isinstance(frame, torch.Tensor):
+        return frame.cuda(non_blocking=True) if not frame.is_cuda else frame
+    return torch.from_numpy(np.ascontiguousarray(frame, dtype=np.float32)).cuda(non_blocking=True)
+
+
+def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
+    """Device pipeline (super_resolution.py:41-200).
+
+    ref_img [H,W], comp_imgs [N-1,H,W]: float32 host arrays (numpy / pinned torch) or CUDA tensors.
+    Returns (num/den as a CUDA tensor [round(s*H), round(s*W), 3] float32, debug_dict) like the reference.
+
+    B200 additions (optional, used by the distributed driver): `frame_ids` restricts the comp loop to a subset of
+    frames (frame sharding) and `reduce_fn(num, den, acc_rob)` is called once after the loop — the one natural
+    reduction point of the pipeline."""
+    verbose_2 = config.verbose >= 2
+    grey_method = config.grey_method
+    if config.mode != "bayer":
+        raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
+    init_alignment_ = timer(init_alignment, verbose_2, "\nInitializing alignment", "Alignment initialized (Total)")
+    init_robustness_ = timer(init_robustness, verbose_2, "\nEstimating ref image local stats", "Local stats estimated (Total)")
+    align_ = timer(align, verbose_2, "\nBeginning alignment", "Image aligned (Total)")
+    compute_robustness_ = timer(compute_robustness, verbose_2, "\nEstimating robustness", "Robustness estimated (Total)")
+    estimate_kernels_ = timer(estimate_kernels, verbose_2, "\nEstimating kernels", "Kernels estimated (Total)")
+    merge_ = timer(merge, verbose_2, "\nAccumulating Image", "Image accumulated (Total)")
+    merge_ref_ = timer(merge_ref, verbose_2, "\nAccumulating ref Img", "Ref Img accumulated (Total)")
+
+    debug_mode = config.debug
+    debug_dict = {"robustness": [], "flow": []}
+    accumulate_r = config.accumulated_robustness_denoiser.enabled or config.robustness.save_mask
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t1 = time.perf_counter()
+
+    cuda_ref_img = _upload(ref_img)
+    cfa_pattern = config.exif.cfa_pattern
+    white_balance = config.exif.white_balance
+    std_curve = _lib.as_device(np.asarray(config.noise_model.std_curve, dtype=np.float64), torch.float64)
+    diff_curve = _lib.as_device(np.asarray(config.noise_model.diff_curve, dtype=np.float64), torch.float64)
+
+    cuda_ref_grey = compute_grey_images(cuda_ref_img, grey_method)
+    ref_pyramid, tyled_pyr, ref_tiled_fft, ref_gradx, ref_grady, ref_hessian = init_alignment_(cuda_ref_grey, config)
+    ref_local_means, ref_local_stds = init_robustness_(cuda_ref_img, cfa_pattern, white_balance, config)
+
+    H, W = cuda_ref_img.shape
+    scale = config.scale
+    output_size = (round(scale * H), round(scale * W))
+    num = torch.zeros((*output_size, 3), dtype=torch.float32, device=dev)
+    den = torch.zeros((*output_size, 3), dtype=torch.float32, device=dev)
+    accumulated_r = torch.zeros((H, W), dtype=torch.float64, device=dev) if accumulate_r else None
+
+    n_images = len(comp_imgs)
+    ids = range(n_images) if frame_ids is None else frame_ids
+    copy_stream = torch.cuda.Stream()
+    compute_stream = torch.cuda.current_stream()
+    pending = {}
+
+    def prefetch(i):   # H2D of frame i on the copy stream, overlapped with compute on the previous frame
+        if i is None or i in pending:
+            return
+        with torch.cuda.stream(copy_stream):
+            t = _upload(comp_imgs[i])
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        pending[i] = (t, ev)
+
+    ids = list(ids)
+    if ids:
+        prefetch(ids[0])
+    for k, im_id in enumerate(ids):
+        prefetch(ids[k + 1] if k + 1 < len(ids) else None)
+        cuda_img, ev = pending.pop(im_id)
+        compute_stream.wait_event(ev)
+        cuda_img.record_stream(compute_stream)
+        cuda_im_grey = compute_grey_images(cuda_img, grey_method)
+        flow = align_(ref_pyramid, tyled_pyr, ref_tiled_fft, ref_gradx, ref_grady, ref_hessian, cuda_im_grey, config)
+        if debug_mode:
+            debug_dict["flow"].append(flow.cpu().numpy())
+        r = compute_robustness_(cuda_img, ref_local_means, ref_local_stds, flow, cfa_pattern, white_balance,
+                                (std_curve, diff_curve), config, acc_rob=accumulated_r if config.robustness.enabled else None)
+        if accumulate_r and not config.robustness.enabled:
+            accumulated_r += r
+        covs = estimate_kernels_(cuda_img, config)
+        merge_(cuda_img, flow, covs, r, num, den, cfa_pattern, config)
+        if debug_mode:
+            debug_dict["robustness"].append(r.cpu().numpy())
+
+    if reduce_fn is not None:
+        reduce_fn(num, den, accumulated_r)
+
+    covs = estimate_kernels_(cuda_ref_img, config)
+    use_acc = accumulated_r if config.accumulated_robustness_denoiser.enabled else None
+    merge_ref_(cuda_ref_img, covs, num, den, cfa_pattern, config, use_acc, fuse_divide=True)   # + utils.divide, :191
+
+    if config.verbose >= 1:
+        torch.cuda.synchronize()
+        s = "\nTotal ellapsed time : "
+        print(s, " " * (50 - len(s)), ": ", round((time.perf_counter() - t1), 2), "seconds")
+    if accumulate_r:
+        debug_dict["accumulated robustness"] = accumulated_r
+    return num, debug_dict
+
+
+def load_burst(burst_path):
+    """Host loader for the drop-in `process()`: a directory (or .npz) holding a RAW burst as arrays.
+    DNG decoding (utils_dng.py) is outside this repository's scope."""
+    p = str(burst_path)
+    if os.path.isdir(p):
+        p = os.path.join(p, "burst.npz")
+    if not os.path.exists(p):
+        raise FileNotFoundError("expected a burst archive at %s (keys: burst [N,H,W] float32 in [0,1], optional "
+                                "cfa_pattern, white_balance, alpha, beta, iso, std_curve, diff_curve)" % p)
+    z = np.load(p)
+    return {k: z[k] for k in z.files}
+
+
+def process(burst_path, config):
+    """Host wrapper (super_resolution.py:203-360): load burst, derive the SNR-based parameters exactly like the
+    reference (mutating `config`), run main(), return (np.ndarray [H*s, W*s, 3], debug_dict).  RAW decoding and the
+    CPU ISP post-process are out of scope: the burst comes from an .npz archive and the output is the normalised
+    linear RGB image the reference hands to raw2rgb.postprocess."""
+    from .config import Config
+    from .noise_model import run_fast_MC
+    data = load_burst(burst_path)
+    burst = np.asarray(data["burst"], dtype=np.float32)
+    ref_raw, raw_comp = burst[0], burst[1:]
+    if config.noise_model.get("alpha", None) is None:
+        if "alpha" not in data:
+            raise ValueError("noise model: alpha/beta neither in the config nor in the burst archive")
+        config.noise_model.update({"alpha": float(data["alpha"]), "beta": float(data["beta"])})
+    alpha, beta = config.noise_model.alpha, config.noise_model.beta
+    if "std_curve" in data:
+        std_curve, diff_curve = np.asarray(data["std_curve"]), np.asarray(data["diff_curve"])
+    else:
+        std_curve, diff_curve = run_fast_MC(alpha, beta)
+    brightness = np.mean(ref_raw)
+    SNR = brightness / std_curve[round(1000 * brightness)]
+    update_snr_config(config, SNR)
+    sanitize_config(config, ref_raw.shape)
+    config.exif = Config.wrap({
+        "cfa_pattern": np.asarray(data.get("cfa_pattern", [[0, 1], [1, 2]])).tolist(),
+        "iso": int(data.get("iso", 100)),
+        "white_balance": np.asarray(data.get("white_balance", [1.0, 1.0, 1.0, 0.0]), dtype=np.float64).tolist()})
+    config.noise_model.update({"std_curve": std_curve.tolist(), "diff_curve": diff_curve.tolist()})
+    ard = config.accumulated_robustness_denoiser
+    ard.enabled = bool(any(x.enabled for x in (ard.median, ard.gauss, ard.merge)))
+    if ard.median.enabled or ard.gauss.enabled:
+        raise NotImplementedError("post-merge frame-count denoisers are out of scope (SURVEY section 2, row 17)")
+    out, debug_dict = main(ref_raw, raw_comp, config)
+    output_image = out.cpu().numpy()
+    if "accumulated robustness" in debug_dict:
+        debug_dict["accumulated robustness"] = debug_dict["accumulated robustness"].cpu().numpy()
+    return output_image, debug_dict

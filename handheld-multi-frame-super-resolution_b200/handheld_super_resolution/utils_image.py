@@ -1,0 +1,79 @@
+"""Image helpers on the hot path — mirrors handheld_super_resolution/utils_image.py of the reference:
+compute_grey_images (:58-115), GAT (:117-170), cuda_downsample (:360-391)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def compute_grey_images(img, method):
+    """Raw -> grey (utils_image.py:58-115).
+
+    "FFT": the ideal half-band low-pass of Alg. 3.  The FFTs are cuFFT calls (torch.fft.rfft2 / irfft2); the
+    reference's fftshift + four masked fills + ifftshift + .real become one in-place band-mask kernel on the half
+    spectrum (hhsr_grey_band_mask), which is mathematically identical for a real input.
+    "decimating": 2x2 mean."""
+    img = _lib.as_device(img)
+    h, w = img.shape
+    if method == "FFT":
+        spec = torch.fft.rfft2(img)
+        _lib.call("hhsr_grey_band_mask", _lib.ptr(spec), h, w, spec.stride(0), spec.stride(1), _lib.stream())
+        return torch.fft.irfft2(spec, s=(h, w))
+    elif method == "decimating":
+        out = torch.empty((h // 2, w // 2), dtype=torch.float32, device=img.device)
+        _lib.call("hhsr_decimate_to_grey", _lib.ptr(img), h, w, _lib.ptr(out), _lib.stream())
+        return out
+    raise NotImplementedError("Computation of gray level on GPU is only supported for FFT")
+
+
+def GAT(image, alpha, beta):
+    """Generalised Anscombe transform (utils_image.py:117-170)."""
+    image = _lib.as_device(image)
+    assert len(image.shape) == 2
+    assert alpha > 0, f"alpha should be positive, got {alpha} (VST is ill defined and kernels would be wrong)"
+    out = torch.empty_like(image)
+    _lib.call("hhsr_gat", _lib.ptr(image), image.numel(), float(alpha), float(beta), _lib.ptr(out), _lib.stream())
+    return out
+
+
+def gaussian_kernel1d(sigma, radius):
+    """The 1-D kernel the reference takes from scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius)
+    (utils_image.py:380), restated so that no private scipy API is needed."""
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return phi / phi.sum()
+
+
+def cuda_downsample(th_img, kernel="gaussian", factor=2):
+    """One pyramid level (utils_image.py:360-391).  th_img: [h,w] (or [1,1,h,w]) CUDA tensor; returns [h2,w2]."""
+    if factor == 1:
+        return th_img
+    if kernel != "gaussian":
+        raise ValueError("please use gaussian kernel")
+    img = _lib.as_device(th_img)
+    img = img.reshape(img.shape[-2], img.shape[-1])
+    radius = int(4 * factor * 0.5 + 0.5)
+    taps = gaussian_kernel1d(factor * 0.5, radius)[::-1].astype(np.float32)
+    h, w = img.shape
+    h2, w2 = (h - 2 * radius) // factor, (w - 2 * radius) // factor
+    if h2 < 1 or w2 < 1:
+        raise ValueError("image of shape %s too small for a pyramid level of factor %d" % ((h, w), factor))
+    out = torch.empty((h2, w2), dtype=torch.float32, device=img.device)
+    _lib.call("hhsr_gauss_downsample", _lib.ptr(img), h, w, int(factor),
+              taps.ctypes.data_as(C.POINTER(C.c_float)), radius, _lib.ptr(out), h2, w2, _lib.stream())
+    return out
+
+
+def computeRMSE(image1, image2):
+    """utils_image.py:408-414."""
+    assert np.array_equal(image1.shape, image2.shape), "images have different sizes"
+    d = image1.astype(np.float64) - image2.astype(np.float64)
+    return np.sqrt(np.mean(d * d))
+
+
+def computePSNR(image, noisyImage):
+    """utils_image.py:417-437 (images in [0,1])."""
+    rmse = computeRMSE(image, noisyImage)
+    return float("inf") if rmse == 0 else 20 * np.log10(1.0 / rmse)

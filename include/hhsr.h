@@ -1,0 +1,135 @@
+/* hhsr.h — C ABI of libhhsr.so: the B200-native (sm_100a) handheld burst super-resolution hot path.
+ *
+ * The reference (Jamy-L/Handheld-Multi-Frame-Super-Resolution) has no FFI layer: its hot path is a set of Python
+ * stage functions that launch Numba-CUDA kernels.  Each entry point below replaces the
+ * device work of one of those stage functions; the reference interface it replaces is cited as
+ * `handheld_super_resolution/<file>:<line>`.  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to call them.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a C-contiguous array unless the parameter is documented "host";
+ *   - images are [rows][cols] float32; flow fields are [ny][nx][2] float32 holding (dx, dy);
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library keeps no device state;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *     and never synchronises;
+ *   - return value: 0 on success, a negative HHSR_E_* code for rejected arguments, a positive cudaError_t when
+ *     a launch failed; hhsr_last_error_string() (thread-local) describes the last failure.
+ */
+#ifndef HHSR_H
+#define HHSR_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HHSR_VERSION 100 /* 0.1.0 */
+
+#define HHSR_E_BADARG (-1)      /* null pointer, non-positive size, misaligned buffer */
+#define HHSR_E_UNSUPPORTED (-2) /* tile size / radius / mode outside what the reference supports */
+
+typedef void *hhsr_stream_t;
+
+int hhsr_version(void);
+const char *hhsr_last_error_string(void);
+
+/* ---- grey image, Alg. 3 (utils_image.py:82-100).  The forward/inverse FFTs stay cuFFT calls made by the host
+ * (torch.fft.rfft2 / irfft2); this applies the reference's band mask to the half spectrum in place:
+ * spec[ky][kx] *= 0.5*(My(ky)Mx(kx) + My(-ky)Mx(-kx)), the Hermitian-symmetrised form of the mask the reference
+ * applies to the full shifted spectrum before taking .real.  spec: [H][W/2+1] complex64 (interleaved re,im) with
+ * strides (stride_y, stride_x) in complex elements — cuFFT-through-torch hands back a column-major spectrum. */
+int hhsr_grey_band_mask(float *spec, int H, int W, long long stride_y, long long stride_x, hhsr_stream_t stream);
+
+/* ---- Gaussian pyramid (alignment.py:74-82, utils_image.py:360-391) */
+/* circular padding of the reference grey image to a multiple of the tile size (alignment.py:26-37) */
+int hhsr_pad_circular(const float *src, int h, int w, float *dst, int hp, int wp, hhsr_stream_t stream);
+/* one pyramid level: separable valid correlation with `taps` (host pointer, 2*radius+1 floats, radius <= 16),
+ * y pass then x pass, keeping only outputs (i*factor, j*factor): dst[h2][w2], h2 = (h-2r)/factor. */
+int hhsr_gauss_downsample(const float *src, int h, int w, int factor, const float *taps_host, int radius,
+                          float *dst, int h2, int w2, hhsr_stream_t stream);
+
+/* ---- ICA initialisation (ICA.py:15-76): central-difference gradients (zero outside) and the per-tile 2x2
+ * Hessian [ny][nx][2][2], ny = h/ts, nx = w/ts. */
+int hhsr_grad_hessian(const float *img, int h, int w, int ts, float *gradx, float *grady, float *hessian,
+                      hhsr_stream_t stream);
+
+/* ---- flow upscaling between pyramid levels (alignment.py:150-172): out = factor * upsample(in, repeat),
+ * zero-padded (or cropped) to [ny_out][nx_out].  mode: 0 nearest, 1 bilinear, 2 bicubic (torch
+ * F.interpolate semantics, align_corners=False). */
+int hhsr_upscale_flow(const float *flow_in, int ny_in, int nx_in, float *flow_out, int ny_out, int nx_out,
+                      int repeat, float factor, int mode, hhsr_stream_t stream);
+
+/* ---- L2 block matching (block_matching.py:20-76, 348-378): per tile, exhaustive search of
+ * sum(m^2) - 2 sum(ref*m) over (2r+1)^2 integer shifts around rint(flow), moving image read with clamped
+ * coordinates, first minimum in v-major order; flow += (u*, v*) in place.  ts in {8,16,32,64}, radius <= 8. */
+int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const float *mov, int mov_h, int mov_w,
+                      float *flow, int ny, int nx, int ts, int radius, hhsr_stream_t stream);
+/* ---- "L1" level as the compiled reference executes it (block_matching.py:78-345): the SAD search
+ * result is discarded and flow <- rint(flow) (half to even).  n = ny*nx*2 floats. */
+int hhsr_bm_l1_compat(float *flow, int n, hhsr_stream_t stream);
+
+/* ---- ICA / Lucas-Kanade refinement (ICA.py:78-481): n_iter Gauss-Newton steps per tile, in place on flow.
+ * ts selects the reference kernel being reproduced: 8 (clamped sampling, fp64 1/det), 16 and 32 (zero fill),
+ * 64 (zero fill + sliding-window row quirk). */
+int hhsr_ica(const float *ref, const float *gradx, const float *grady, int ref_h, int ref_w,
+             const float *hessian, const float *mov, int mov_h, int mov_w, float *flow, int ny, int nx, int ts,
+             int n_iter, hhsr_stream_t stream);
+
+/* ---- steering kernels, Alg. 5 (kernels.py:29-243, linalg.py:86-185, utils_image.py:117-170,346-357): fused
+ * GAT -> 2x2 decimation -> gradients -> structure tensor -> eigen-decomposition -> covariance.
+ * covs: [H/2][W/2][2][2].  law: 0 hard_threshold, 1 linear. */
+int hhsr_estimate_kernels(const float *raw, int H, int W, double alpha, double beta, double k_detail,
+                          double k_denoise, double D_th, double D_tr, double k_stretch, double k_shrink, int law,
+                          float *covs, hhsr_stream_t stream);
+
+/* stand-alone pieces of the same stage, kept because the reference exposes them (utils_image.py:117-170 GAT,
+ * utils_image.py:346-357 compute_grey_images(method="decimating")); hhsr_estimate_kernels does not need them. */
+int hhsr_gat(const float *img, size_t n, double alpha, double beta, float *out, hhsr_stream_t stream);
+int hhsr_decimate_to_grey(const float *img, int H, int W, float *out, hhsr_stream_t stream);
+
+/* ---- robustness, Alg. 6-9 (robustness.py).  cfa_host: 4 ints (row-major 2x2 channel ids), wb_host: 3 doubles. */
+/* guide image + 3x3 local statistics at half resolution (robustness.py:173-294): means/vars [3][H/2][W/2];
+ * vars may be NULL. */
+int hhsr_guide_stats(const float *raw, int H, int W, const int *cfa_host, const double *wb_host, float *means,
+                     float *vars, hhsr_stream_t stream);
+/* x2 Dodgson upsampling (+ tile-flow warp when flow != NULL) of a [3][h][w] statistic to [3][2h][2w]
+ * (robustness.py:296-418); +inf where the source position leaves the guide image. */
+int hhsr_upscale_warp_stats(const float *lr, int h, int w, const float *flow, int ny, int nx, int ts, float *hr,
+                            hhsr_stream_t stream);
+/* fused per-pixel robustness (robustness.py:421-639): warped Dodgson upsampling of the comp guide means,
+ * |mean difference|, noise-model shrinkage, flow-irregularity factor S and threshold -> R [H][W].
+ * ref_means/ref_vars: [3][H][W] from hhsr_upscale_warp_stats; curves: float64 device arrays of n_curve entries. */
+int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_vars, int H, int W,
+                    const float *flow, int ny, int nx, int ts, const double *std_curve, const double *diff_curve,
+                    int n_curve, double t, double s1, double s2, double Mt, float *R, hhsr_stream_t stream);
+/* 5x5 edge-replicated local minimum (robustness.py:641-687); when acc_rob != NULL also acc_rob += r
+ * (utils.py:93-120, float64 accumulator). */
+int hhsr_local_min5(const float *R, int H, int W, float *r, double *acc_rob, hhsr_stream_t stream);
+
+/* ---- merge, Alg. 4 (merge.py:236-434): accumulate one aligned comp frame into num/den [Hs][Ws][3].
+ * iso: 0 steerable kernel, 1 isotropic. */
+int hhsr_merge_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
+                          const float *covs, const float *r, float *num, float *den, int Hs, int Ws, double scale,
+                          const int *cfa_host, int iso, hhsr_stream_t stream);
+/* Same arithmetic for K comp frames in one pass over the accumulators (frame order preserved per pixel).
+ * raws/flows/covs/rs: HOST arrays of K device pointers. */
+int hhsr_merge_accumulate_batch(const float *const *raws, const float *const *flows, const float *const *covs,
+                                const float *const *rs, int K, int H, int W, int ny, int nx, int ts, float *num,
+                                float *den, int Hs, int Ws, double scale, const int *cfa_host, int iso,
+                                hhsr_stream_t stream);
+/* ---- merge of the reference frame, Alg. 11 (merge.py:22-233).  acc_rob (float64 [H][W]) may be NULL; when given,
+ * the accumulated-robustness denoiser rules apply (widened window / overwrite).  fuse_divide != 0 additionally
+ * performs utils.divide (num <- num/den) in the same pass. */
+int hhsr_merge_ref(const float *raw, int H, int W, const float *covs, float *num, float *den, int Hs, int Ws,
+                   double scale, const int *cfa_host, int iso, const double *acc_rob, int max_frame_count,
+                   int rad_max, double max_multiplier, int fuse_divide, hhsr_stream_t stream);
+
+/* ---- element-wise helpers (utils.py:62-120) */
+int hhsr_divide(float *num, const float *den, size_t n, hhsr_stream_t stream);
+int hhsr_add_f64_f32(double *A, const float *B, size_t n, hhsr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HHSR_H */

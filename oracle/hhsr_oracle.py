@@ -654,7 +654,7 @@ def accumulate_ref(raw, covs, num, den, cfa, scale, iso_kernel=False, acc_rob=No
                                      covs[fy0, cx1, a, b].astype(F64) * rx * (1 - ry) +
                                      covs[cy1, fx0, a, b].astype(F64) * (1 - rx) * ry +
                                      covs[cy1, cx1, a, b].astype(F64) * rx * ry).astype(F32)
-            det = ic[..., 0, 0] * ic[..., 1, 1] - ic[..., 0, 1] * ic[..., 1, 0]        # f32
+            det = fma32(ic[..., 0, 0], ic[..., 1, 1], -(ic[..., 0, 1] * ic[..., 1, 0]))   # f32, contracted by NVVM
             good = np.abs(det.astype(F64)) > EPSILON_DIV
             det_i = 1 / det.astype(F64)
             i00 = np.where(good, (ic[..., 1, 1] * det_i).astype(F32), F32(1))

@@ -1,0 +1,430 @@
+"""GPU parity tests (`-m gpu`): every CUDA stage of libhhsr.so, called through the product's Python surface
+(ctypes -> C ABI), against (1) the golden vectors produced by the unmodified reference on a B200
+(tests/golden/*.npz) and (2) the NumPy oracle on the same inputs.  Tolerances are stated per assertion; integer
+block-matching offsets must be bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import CFA, WB, attr_cfg, curves, load, maxdiff, plain_cfg, reldiff
+
+pytestmark = pytest.mark.gpu
+
+REPORT = {}
+
+
+def dev(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def record(name, value):
+    REPORT[name] = value
+    out = os.path.join(os.path.dirname(__file__), "..", "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    json.dump(REPORT, open(os.path.join(out, "gpu_parity_report.json"), "w"), indent=1)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    return load("tiny_pipeline.npz")
+
+
+@pytest.fixture(scope="module")
+def stage():
+    return load("stage_cases.npz")
+
+
+@pytest.fixture(scope="module")
+def alcases():
+    return load("alignment_cases.npz")
+
+
+def test_library_loaded():
+    from handheld_super_resolution import _lib
+    assert _lib.lib().hhsr_version() == 100
+
+
+# ------------------------------------------------------------------------------------------------ grey + pyramid
+def test_grey_fft(tiny):
+    from handheld_super_resolution.utils_image import compute_grey_images
+    for i in range(3):
+        g = host(compute_grey_images(dev(tiny["burst"][i]), "FFT"))
+        d = maxdiff(g, tiny["grey_%d" % i])
+        record("grey_%d" % i, d)
+        assert d < 2e-6          # cuFFT r2c/c2r vs the reference's c2c: float32 rounding only
+
+
+def test_grey_fft_odd_sizes():
+    import hhsr_oracle as O
+    from handheld_super_resolution.utils_image import compute_grey_images
+    rng = np.random.default_rng(0)
+    for shape in [(50, 66), (46, 62), (48, 64), (37, 51)]:
+        img = rng.random(shape).astype(np.float32)
+        d = maxdiff(host(compute_grey_images(dev(img), "FFT")), O.grey_fft(img))
+        assert d < 2e-6, (shape, d)
+
+
+def test_pyramid_and_init_alignment(tiny):
+    from handheld_super_resolution.alignment import init_alignment
+    cfg = attr_cfg(tiny["cfg_json"])
+    pyr, _, grid, gx, gy, hs = init_alignment(dev(tiny["grey_0"]), cfg)
+    for i in range(3):
+        d = maxdiff(host(pyr[i]), tiny["pyr_0_c%d" % i])
+        record("pyr_c%d" % i, d)
+        assert d < 1e-6
+        assert maxdiff(host(gx[i]), tiny["ref_gradx_c%d" % i]) < 2e-6
+        assert maxdiff(host(gy[i]), tiny["ref_grady_c%d" % i]) < 2e-6
+        r = reldiff(host(hs[i]), tiny["ref_hessian_c%d" % i], floor=1.0)
+        record("hessian_rel_c%d" % i, r)
+        assert r < 5e-6          # parallel vs sequential float32 sum of ts^2 products
+
+
+def test_moving_pyramid(tiny):
+    from handheld_super_resolution.alignment import build_gaussian_pyramid
+    pyr = build_gaussian_pyramid(dev(tiny["grey_1"]), [1, 2, 2])
+    for i in range(3):
+        assert maxdiff(host(pyr[i]), tiny["pyr_1_c%d" % i]) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ alignment
+def test_alignment_levels_against_golden(tiny):
+    """Feed the reference's own level inputs to each of our level kernels."""
+    from handheld_super_resolution import alignment as AL
+    cfg = attr_cfg(tiny["cfg_json"])
+    ref = AL.init_alignment(dev(tiny["grey_0"]), cfg)
+    for f in (1, 2):
+        mpyr = AL.build_gaussian_pyramid(dev(tiny["grey_%d" % f]), cfg.block_matching.tuning.factors)
+        for i, l in enumerate((2, 1, 0)):
+            flow = dev(tiny["flow_f%d_l%d_in" % (f, l)])
+            if cfg.block_matching.tuning.metrics[l] == "L2":
+                AL.align_lvl_block_matching_L2(ref[1][i], ref[2][i], mpyr[i], flow, l, cfg)
+            else:
+                AL.align_lvl_block_matching_L1(ref[0][i], mpyr[i], flow, l, cfg)
+            assert np.array_equal(host(flow), tiny["flow_f%d_l%d_bm" % (f, l)]), "block matching offsets differ"
+            AL.align_lvl_ica(ref[0][i], ref[3][i], ref[4][i], ref[5][i], mpyr[i], flow, l, cfg)
+            d = maxdiff(host(flow), tiny["flow_f%d_l%d_ica" % (f, l)])
+            record("ica_f%d_l%d" % (f, l), d)
+            assert d < 2e-5      # px; reduction order through 3 Gauss-Newton steps
+        # flow upscaling
+        for l in (1, 0):
+            up = AL.upscale_lvl(dev(tiny["flow_f%d_l%d_ica" % (f, l + 1)]), tiny["flow_f%d_l%d_up" % (f, l)].shape[:2], l, cfg)
+            assert np.array_equal(host(up), tiny["flow_f%d_l%d_up" % (f, l)])
+
+
+def test_align_end_to_end(tiny):
+    from handheld_super_resolution import alignment as AL
+    cfg = attr_cfg(tiny["cfg_json"])
+    ref = AL.init_alignment(dev(tiny["grey_0"]), cfg)
+    for f in (1, 2):
+        flow = host(AL.align(*ref, dev(tiny["grey_%d" % f]), cfg))
+        d = maxdiff(flow, tiny["flow_f%d" % f])
+        record("flow_f%d" % f, d)
+        assert d < 1e-4          # px
+
+
+@pytest.mark.parametrize("ts", [8, 16, 32, 64])
+def test_ica_and_bm_per_tile_size(alcases, ts):
+    from handheld_super_resolution import ICA, block_matching as BM
+    c = alcases
+    cfg = attr_cfg(tile_sizes=[ts, ts, ts], search_radii=[4, 4, 4])
+    ref, mov = dev(c["ref_%d" % ts]), dev(c["mov_%d" % ts])
+    gx, gy, hess = ICA.init_ica(ref, ts, cfg)
+    assert maxdiff(host(gx), c["gx_%d" % ts]) < 1e-6 and maxdiff(host(gy), c["gy_%d" % ts]) < 1e-6
+    # the reference adds ts^2 products sequentially in float32 (ICA.py:54-69); error grows with the tile size
+    assert reldiff(host(hess), c["hess_%d" % ts], floor=1.0) < (5e-5 if ts == 64 else 5e-6)
+    flow = dev(c["flow0_%d" % ts])
+    ICA.align_lvl_ica(ref, dev(c["gx_%d" % ts]), dev(c["gy_%d" % ts]), dev(c["hess_%d" % ts]), mov, flow, 0, cfg)
+    d = maxdiff(host(flow), c["ica_%d" % ts])
+    record("ica_ts%d" % ts, d)
+    assert d < 2e-5
+    flow = dev(c["flow0_%d" % ts])
+    BM.align_lvl_block_matching_L2(ref, None, mov, flow, 0, cfg)
+    assert np.array_equal(host(flow), c["bm2_%d" % ts]), "L2 offsets differ from the reference (ts=%d)" % ts
+    if ts in (32, 64):
+        cfg.block_matching.tuning.search_radii = [1, 1, 1]
+        flow = dev(c["flow0_%d" % ts])
+        BM.align_lvl_block_matching_L1(ref, mov, flow, 0, cfg)
+        assert np.array_equal(host(flow), c["bm1_%d" % ts])
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear", "bicubic"])
+def test_upscale_modes(alcases, mode):
+    from handheld_super_resolution import alignment as AL
+    cfg = attr_cfg(tile_sizes=[32, 32, 32, 16], factors=[1, 2, 4, 4], flow_upscale_mode=mode)
+    for l in (2, 0):
+        up = host(AL.upscale_lvl(dev(alcases["up_in"]), (11, 15), l, cfg))
+        assert maxdiff(up, alcases["up_l%d_%s" % (l, mode)]) < 1e-5
+
+
+def test_bm_l2_exact_vs_oracle_random():
+    """Integer offsets bit-exact against the oracle on seeded textured tiles with arbitrary start flows."""
+    import hhsr_oracle as O
+    from handheld_super_resolution import block_matching as BM
+    rng = np.random.default_rng(3)
+    for ts, r in [(16, 4), (32, 4), (8, 2), (64, 4)]:
+        ny, nx = 3, 4
+        ref = rng.random((ny * ts, nx * ts)).astype(np.float32)
+        mov = np.roll(ref, (2, -3), (0, 1))[:, :nx * ts - 5].copy() + 0.05 * rng.random((ny * ts, nx * ts - 5)).astype(np.float32)
+        flow0 = rng.uniform(-3, 3, (ny, nx, 2)).astype(np.float32)
+        want = O.bm_l2(ref, mov, flow0, ts, r)
+        cfg = attr_cfg(tile_sizes=[ts], search_radii=[r])
+        flow = dev(flow0)
+        BM.align_lvl_block_matching_L2(dev(ref), None, dev(mov), flow, 0, cfg)
+        assert np.array_equal(host(flow), want)
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+def test_estimate_kernels(tiny, stage):
+    from handheld_super_resolution.kernels import estimate_kernels
+    cfg = attr_cfg(tiny["cfg_json"])
+    for k, img in ((1, tiny["burst"][1]), (2, tiny["burst"][2]), (3, tiny["burst"][0])):
+        c = host(estimate_kernels(dev(img), cfg))
+        d, r = maxdiff(c, tiny["covs_%d" % k]), reldiff(c, tiny["covs_%d" % k])
+        record("covs_%d" % k, [d, r])
+        assert d < 1e-6 and r < 5e-6
+    for law in ("linear", "hard_threshold"):
+        cfg.merging.selection_law = law
+        c = host(estimate_kernels(dev(stage["raw_flat"]), cfg))
+        assert reldiff(c, stage["covs_flat_" + law]) < 5e-6
+        assert maxdiff(c, stage["covs_flat_" + law]) < 1e-6      # asserts the NaN pattern too
+        c = host(estimate_kernels(dev(stage["raw"]), cfg))
+        assert reldiff(c, stage["covs_" + law]) < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------ robustness
+def test_init_robustness(tiny, stage):
+    from handheld_super_resolution import robustness as RB
+    cfg = attr_cfg(tiny["cfg_json"])
+    m, s = RB.init_robustness(dev(tiny["burst"][0]), CFA, WB, cfg)
+    assert maxdiff(host(m), tiny["ref_means"]) < 1e-7
+    assert maxdiff(host(s), tiny["ref_stds"]) < 1e-7
+    lm, ls = RB.compute_guide_stats(dev(stage["raw"]), CFA, WB)
+    assert maxdiff(host(lm), stage["lmeans_f1"]) < 1e-7 and maxdiff(host(ls), stage["lstds_f1"]) < 1e-7
+
+
+def test_compute_robustness(tiny, stage):
+    from handheld_super_resolution import robustness as RB
+    cfg = attr_cfg(tiny["cfg_json"])
+    std, diff = curves()
+    for f in (1, 2):
+        r, R = RB.compute_robustness(dev(tiny["burst"][f]), dev(tiny["ref_means"]), dev(tiny["ref_stds"]),
+                                     dev(tiny["flow_f%d" % f]), CFA, WB, (std, diff), cfg, return_R=True)
+        dR, dr = maxdiff(host(R), tiny["R_f%d" % f]), maxdiff(host(r), tiny["r_f%d" % f])
+        record("robustness_f%d" % f, [dR, dr])
+        assert dR < 2e-6 and dr < 2e-6
+        assert np.all(host(r)[:3, :] == 0) and np.all(host(r)[:, :3] == 0)      # SURVEY Q6 band
+    # irregular flow (S = s1 tiles, out-of-frame warps)
+    m, s = RB.init_robustness(dev(stage["ref"]), CFA, WB, cfg)
+    r = RB.compute_robustness(dev(stage["raw"]), m, s, dev(stage["flow_irreg"]), CFA, WB, (std, diff), cfg)
+    assert maxdiff(host(r), stage["r_irreg"]) < 2e-6
+    # accumulate r into a float64 map (utils.add fused into the last launch)
+    acc = torch.zeros(stage["raw"].shape, dtype=torch.float64, device="cuda")
+    RB.compute_robustness(dev(stage["raw"]), m, s, dev(stage["flow_irreg"]), CFA, WB, (std, diff), cfg, acc_rob=acc)
+    assert np.array_equal(host(acc), stage["r_irreg"].astype(np.float64))
+    cfg.robustness.enabled = False
+    assert torch.all(RB.compute_robustness(dev(stage["raw"]), m, s, dev(stage["flow_irreg"]), CFA, WB, (std, diff), cfg) == 1)
+
+
+# ------------------------------------------------------------------------------------------------ merge
+MERGE_TOL = 2e-5    # abs on num/den values of O(1): float32 weights (ex2.approx) vs the reference's float64
+
+
+@pytest.mark.parametrize("scale,kern", [(1, "steerable"), (1.5, "steerable"), (2, "steerable"), (3, "steerable"),
+                                        (1.5, "iso"), (2, "iso")])
+def test_merge_scales(stage, scale, kern):
+    from handheld_super_resolution import merge as MG
+    cfg = attr_cfg(scale=scale, kernel=kern)
+    H, W = stage["raw"].shape
+    hs, ws = round(scale * H), round(scale * W)
+    num = torch.zeros((hs, ws, 3), device="cuda")
+    den = torch.zeros((hs, ws, 3), device="cuda")
+    MG.merge(dev(stage["raw"]), dev(stage["flow_irreg"]), dev(stage["covs1"]), dev(stage["r_rand"]), num, den, CFA, cfg)
+    tag = "s%s_%s" % (str(scale).replace(".", "p"), kern)
+    dn, dd = maxdiff(host(num), stage["merge_num_" + tag]), maxdiff(host(den), stage["merge_den_" + tag])
+    record("merge_" + tag, [dn, dd])
+    assert dn < MERGE_TOL and dd < MERGE_TOL
+    MG.merge_ref(dev(stage["ref"]), dev(stage["covs_ref"]), num, den, CFA, cfg)
+    dn, dd = maxdiff(host(num), stage["mergeref_num_" + tag]), maxdiff(host(den), stage["mergeref_den_" + tag])
+    record("mergeref_" + tag, [dn, dd])
+    assert dn < MERGE_TOL and dd < MERGE_TOL
+
+
+def test_merge_ref_alone_is_tight(stage):
+    """merge_ref keeps the reference's float64 arithmetic: starting from the golden accumulators it must agree to
+    float32 rounding."""
+    from handheld_super_resolution import merge as MG
+    for scale in (1, 1.5, 2, 3):
+        cfg = attr_cfg(scale=scale)
+        tag = "s%s_steerable" % str(scale).replace(".", "p")
+        num, den = dev(stage["merge_num_" + tag]), dev(stage["merge_den_" + tag])
+        MG.merge_ref(dev(stage["ref"]), dev(stage["covs_ref"]), num, den, CFA, cfg)
+        assert maxdiff(host(num), stage["mergeref_num_" + tag]) < 2e-6      # values up to ~5: a few float32 ulps
+        assert maxdiff(host(den), stage["mergeref_den_" + tag]) < 2e-6
+
+
+def test_merge_ref_acc_rob_mode(stage):
+    from handheld_super_resolution import merge as MG
+    cfg = attr_cfg(scale=2)
+    cfg.accumulated_robustness_denoiser.enabled = True
+    cfg.accumulated_robustness_denoiser.merge.enabled = True
+    num, den = dev(stage["merge_num_s2_steerable"]), dev(stage["merge_den_s2_steerable"])
+    MG.merge_ref(dev(stage["ref"]), dev(stage["covs_ref"]), num, den, CFA, cfg, dev(stage["acc_rob"], torch.float64))
+    # 5x5 window with weights widened x8: den reaches ~20, so a few float32 ulps are ~5e-6
+    assert maxdiff(host(num), stage["mergeref_accrob_num"]) < 1e-5
+    assert maxdiff(host(den), stage["mergeref_accrob_den"]) < 1e-5
+
+
+def test_merge_nan_covariances(stage):
+    from handheld_super_resolution import merge as MG
+    cfg = attr_cfg(scale=2)
+    H, W = stage["raw_flat"].shape
+    num = torch.zeros((2 * H, 2 * W, 3), device="cuda")
+    den = torch.zeros((2 * H, 2 * W, 3), device="cuda")
+    MG.merge(dev(stage["raw_flat"]), dev(stage["flow_irreg"]), dev(stage["covs_flat_linear"]), dev(stage["r_rand"]), num, den, CFA, cfg)
+    MG.merge_ref(dev(stage["raw_flat"]), dev(stage["covs_flat_linear"]), num, den, CFA, cfg)
+    assert maxdiff(host(num), stage["merge_flat_num"]) < MERGE_TOL
+    assert maxdiff(host(den), stage["merge_flat_den"]) < MERGE_TOL
+
+
+def test_merge_batch_equals_sequential(tiny):
+    """The K-frame batched merge is bit-identical to K single-frame merges in the same order."""
+    from handheld_super_resolution import merge as MG
+    cfg = attr_cfg(tiny["cfg_json"])
+    raws = [dev(tiny["burst"][f]) for f in (1, 2)]
+    flows = [dev(tiny["flow_f%d" % f]) for f in (1, 2)]
+    covs = [dev(tiny["covs_%d" % f]) for f in (1, 2)]
+    rs = [dev(tiny["r_f%d" % f]) for f in (1, 2)]
+    shape = tiny["num_comp"].shape
+    n1, d1 = torch.zeros(shape, device="cuda"), torch.zeros(shape, device="cuda")
+    for k in range(2):
+        MG.merge(raws[k], flows[k], covs[k], rs[k], n1, d1, CFA, cfg)
+    n2, d2 = torch.zeros(shape, device="cuda"), torch.zeros(shape, device="cuda")
+    MG.merge_batch(raws, flows, covs, rs, n2, d2, CFA, cfg)
+    assert torch.equal(n1, n2) and torch.equal(d1, d2)
+    assert maxdiff(host(n1), tiny["num_comp"]) < MERGE_TOL and maxdiff(host(d1), tiny["den_comp"]) < MERGE_TOL
+
+
+def test_divide_and_add():
+    from handheld_super_resolution.utils import add, divide
+    g = torch.Generator(device="cuda").manual_seed(0)
+    num = torch.rand((37, 53, 3), device="cuda", generator=g)
+    den = torch.rand((37, 53, 3), device="cuda", generator=g)
+    den[3, 4] = 0
+    num[3, 4, 0] = 0
+    want = num / den
+    divide(num, den)
+    assert torch.equal(torch.nan_to_num(num, nan=-1.0), torch.nan_to_num(want, nan=-1.0))
+    assert torch.isnan(num[3, 4, 0])                                           # 0/0 -> NaN
+    A = torch.zeros((17, 19), dtype=torch.float64, device="cuda")
+    B = torch.rand((17, 19), device="cuda", generator=g)
+    add(A, B)
+    add(A, B)
+    assert torch.equal(A, B.double() * 2)
+
+
+# ------------------------------------------------------------------------------------------------ whole pipeline
+PIPE_TOL = 1e-4     # abs on the normalised image in [0,1], identical NaN set
+
+
+def test_main_tiny_against_golden(tiny):
+    from handheld_super_resolution import main
+    cfg = attr_cfg(tiny["cfg_json"])
+    out, dbg = main(tiny["burst"][0], tiny["burst"][1:], cfg)
+    with np.errstate(all="ignore"):
+        want = tiny["num_final"] / tiny["den_final"]
+    d = maxdiff(host(out), want)
+    record("main_tiny", d)
+    assert d < PIPE_TOL
+    assert np.array_equal(host(dbg["accumulated robustness"]), tiny["acc_rob"]) or \
+        maxdiff(host(dbg["accumulated robustness"]), tiny["acc_rob"]) < 1e-5
+
+
+def test_main_medium_against_golden():
+    """700x740, default pyramid [1,2,4,4]: flows of every level + crops of the output (fixture stores crops)."""
+    from handheld_super_resolution import main
+    from handheld_super_resolution import alignment as AL
+    from handheld_super_resolution.utils_image import compute_grey_images
+    m = load("medium_pipeline.npz")
+    burst = m["burst_u16"].astype(np.float32) / np.float32(16383.0)
+    cfg = attr_cfg(m["cfg_json"])
+    ref = AL.init_alignment(compute_grey_images(dev(burst[0]), "FFT"), cfg)
+    mism = 0
+    for f in (1, 2):
+        flow = host(AL.align(*ref, compute_grey_images(dev(burst[f]), "FFT"), cfg))
+        d = np.abs(flow - m["flow_f%d" % f])
+        mism += int((d > 0.5).sum())
+        record("medium_flow_f%d" % f, float(d.max()))
+        assert d.max() < 1e-4
+    assert mism == 0
+    out, _ = main(burst[0], burst[1:], cfg)
+    out = host(out)
+    H, W = out.shape[:2]
+    size = 48
+    cy, cx = (H - size) // 2, (W - size) // 2
+    crops = dict(tl=out[:size, :size], tr=out[:size, W - size:], bl=out[H - size:, :size], br=out[H - size:, W - size:],
+                 c=out[cy:cy + size, cx:cx + size])
+    worst = 0.0
+    for k, v in crops.items():
+        worst = max(worst, maxdiff(v, m["out__" + k]))
+    record("main_medium", worst)
+    assert worst < PIPE_TOL
+    assert int(np.isnan(out).sum()) == int(m["out_nan"])
+    assert np.abs(np.nanmean(out.astype(np.float64), axis=(0, 1)) - m["out_mean"]).max() < 1e-6
+
+
+def test_main_matches_oracle_other_configs():
+    """Configs the goldens do not cover, against the pinned oracle: scale 1.5, iso kernel, hard threshold,
+    robustness off."""
+    import hhsr_oracle as O
+    from handheld_super_resolution import main
+    from handheld_super_resolution.synthetic import synth_burst
+    burst, _ = synth_burst(3, 96, 128, seed=4, max_shift=2.0, quantize_bits=12)
+    for over in (dict(scale=1.5), dict(kernel="iso"), dict(selection_law="hard_threshold"), dict(robustness_enabled=False)):
+        kw = dict(scale=2, tile_size=16, tile_sizes=[16, 16, 8], factors=[1, 2, 2], metrics=["L2", "L2", "L2"],
+                  search_radii=[2, 4, 4])
+        kw.update(over)
+        want, _ = O.main(burst[0], burst[1:], plain_cfg(**kw))
+        out, _ = main(burst[0], burst[1:], attr_cfg(**kw))
+        d = maxdiff(host(out), want)
+        record("main_vs_oracle_%s" % list(over.items())[0][1], d)
+        assert d < PIPE_TOL, over
+
+
+def test_properties_full_size():
+    """Size-independent properties at a BASELINE.json shape (12 MP, scale 2, 3 frames):
+    (1) identical frames and zero flow -> r == 1 outside the 3-px band and output ~ demosaiced reference;
+    (2) constant image -> output equals the constant wherever den > 0;
+    (3) merge linearity: merging a frame with r and then with r' equals merging once with r + r'."""
+    from handheld_super_resolution import main, merge as MG
+    from handheld_super_resolution.kernels import estimate_kernels
+    from handheld_super_resolution.synthetic import synth_burst
+    H, W = 3000, 4000
+    cfg = attr_cfg(scale=2, tile_sizes=[32, 32, 32, 16], factors=[1, 2, 4, 4], metrics=["L1", "L2", "L2", "L2"],
+                   search_radii=[1, 4, 4, 4])
+    const = np.full((H, W), 0.5, np.float32)
+    out, dbg = main(const, np.stack([const, const]), cfg)
+    o = host(out)
+    fin = np.isfinite(o)
+    assert fin.mean() > 0.999 and np.abs(o[fin] - 0.5).max() < 1e-6
+    del out, o
+    burst, _ = synth_burst(1, H, W, seed=5, device="cuda", as_numpy=False)
+    raw = burst[0]
+    covs = estimate_kernels(raw, cfg)
+    flow = torch.zeros((94, 125, 2), device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    r1 = torch.rand((H, W), device="cuda", generator=g) * 0.5
+    r2 = torch.rand((H, W), device="cuda", generator=g) * 0.5
+    shape = (2 * H, 2 * W, 3)
+    n1, d1 = torch.zeros(shape, device="cuda"), torch.zeros(shape, device="cuda")
+    MG.merge(raw, flow, covs, r1, n1, d1, CFA, cfg)
+    MG.merge(raw, flow, covs, r2, n1, d1, CFA, cfg)
+    n2, d2 = torch.zeros(shape, device="cuda"), torch.zeros(shape, device="cuda")
+    MG.merge(raw, flow, covs, r1 + r2, n2, d2, CFA, cfg)
+    assert (n1 - n2).abs().max().item() < 2e-6 and (d1 - d2).abs().max().item() < 2e-6
