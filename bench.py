@@ -1,0 +1,332 @@
+"""Benchmark of the burst super-resolution hot path (BASELINE.json metric: output MPix/s for a 20-frame 12 MP
+Bayer burst merged to 48 MP, scale 2; plus the merge kernel's achieved HBM GB/s against the measured peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repository's CUDA path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # frame-sharded, one rank per GPU
+    python bench.py --impl reference [...]                           # CPU arm: the oracle port on the host cores
+
+A "step" is one whole burst through main(): reference-side products, then every comp frame aligned, weighted
+and merged, reference merge and normalisation.  `value` times the step with the burst already resident in HBM;
+`e2e` times the same call with the burst in pinned host memory (H2D of every frame and D2H of the 48 MP result
+inside the timed region).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "handheld-multi-frame-super-resolution_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {   # BASELINE.json configs
+    "20x12MP_s2": dict(n=20, H=3000, W=4000, scale=2),
+    "8x12MP_s2": dict(n=8, H=3000, W=4000, scale=2),
+    "13x12MP_s3": dict(n=13, H=3000, W=4000, scale=3),
+    "20x50MP_s2": dict(n=20, H=6144, W=8192, scale=2),
+    "2x256_s1": dict(n=2, H=256, W=256, scale=1),
+}
+
+
+def make_config(scale, H, W):
+    """configs/default.yaml + the benchmark settings of SURVEY section 8d: tile_size 32 explicit, ISO-100 noise
+    model, RGGB, SNR-derived merge constants (SNR clips to 30 on the synthetic burst)."""
+    from handheld_super_resolution.config import Config, load_config
+    from handheld_super_resolution.noise_model import run_fast_MC
+    from handheld_super_resolution.params import sanitize_config, update_snr_config
+    from handheld_super_resolution.synthetic import ALPHA_ISO100, BETA_ISO100, CFA_RGGB, WHITE_BALANCE
+    cfg = load_config(overrides={"scale": scale, "verbose": 0, "block_matching": {"tuning": {"tile_size": 32}}})
+    if min(H, W) < 673:   # default factors need >= 673 px; small plumbing config uses [1,2,2,2]
+        cfg.block_matching.tuning.factors = [1, 2, 2, 2]
+    cfg.noise_model.alpha, cfg.noise_model.beta = ALPHA_ISO100, BETA_ISO100
+    std_curve, diff_curve = run_fast_MC(ALPHA_ISO100, BETA_ISO100, seed=0, n_patches=20000)
+    update_snr_config(cfg, 30.0)
+    cfg.exif = Config.wrap({"cfa_pattern": CFA_RGGB, "iso": 100, "white_balance": WHITE_BALANCE})
+    cfg.noise_model.std_curve, cfg.noise_model.diff_curve = std_curve, diff_curve
+    cfg.accumulated_robustness_denoiser.enabled = False
+    sanitize_config(cfg, (H, W))
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def merge_algorithmic_bytes(H, W, scale, ny, nx):
+    """SURVEY section 8d / DESIGN.md: per comp frame, one accumulator pass: num+den read+write (48 B per HR pixel)
+    + raw, r, covariances (4 + 4 + 16/4 = 12 B per LR pixel) + the tile flow."""
+    hs, ws = round(scale * H), round(scale * W)
+    return hs * ws * 48 + H * W * 12 + ny * nx * 8
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the NumPy oracle (a port of the reference; the reference itself is Numba-CUDA only) on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def _oracle_frame(args):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hhsr_oracle as O
+    ref, rm, rs, img, cfg = args
+    cfa, wb = cfg["exif"]["cfa_pattern"], cfg["exif"]["white_balance"]
+    flow = O.align(ref, O.grey_fft(img), cfg)
+    r = O.compute_robustness(img, rm, rs, flow, cfa, wb, cfg["noise_model"]["std_curve"], cfg["noise_model"]["diff_curve"], cfg)
+    covs = O.estimate_kernels(img, cfg)
+    H, W = img.shape
+    s = cfg["scale"]
+    num = np.zeros((round(s * H), round(s * W), 3), np.float32)
+    den = np.zeros_like(num)
+    O.accumulate(img, flow, covs, r, num, den, cfa, s, cfg["block_matching"]["tuning"]["tile_size"])
+    return num, den
+
+
+def oracle_step(burst, cfg, pool):
+    """One burst through the oracle, comp frames spread over the pool's processes."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hhsr_oracle as O
+    cfa, wb = cfg["exif"]["cfa_pattern"], cfg["exif"]["white_balance"]
+    ref = O.init_alignment(O.grey_fft(burst[0]), cfg)
+    rm, rs = O.init_robustness(burst[0], cfa, wb)
+    jobs = [(ref, rm, rs, img, cfg) for img in burst[1:]]
+    parts = pool.map(_oracle_frame, jobs) if pool is not None else [_oracle_frame(j) for j in jobs]
+    num = sum(p[0] for p in parts)
+    den = sum(p[1] for p in parts)
+    O.accumulate_ref(burst[0], O.estimate_kernels(burst[0], cfg), num, den, cfa, cfg["scale"])
+    return O.divide(num, den)
+
+
+def cpu_sample(wl, n_frames, crop, cores):
+    """Bounded sample of the workload for the CPU arm: an n_frames x crop x crop burst from the same generator, same
+    config.  Returns (burst, plain cfg, scaling) with scaling = (sample out MPix) * (n_frames / workload frames): work
+    is proportional to pixels x frames, so value = scaling / seconds is the workload-equivalent output MPix/s."""
+    from handheld_super_resolution.config import to_plain
+    from handheld_super_resolution.synthetic import synth_burst
+    burst, _ = synth_burst(n_frames, crop, crop, seed=0)
+    cfg = to_plain(make_config(wl["scale"], crop, crop))
+    out_mpix = round(wl["scale"] * crop) ** 2 / 1e6
+    return burst, cfg, out_mpix * n_frames / wl["n"]
+
+
+def run_reference_arm(args, wl, wl_name):
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_frames, crop = 4, 704
+    burst, cfg, scaling = cpu_sample(wl, n_frames, crop, cores)
+    nproc = min(cores, n_frames - 1)
+    pool = mp.get_context("fork").Pool(nproc) if nproc > 1 else None
+    for _ in range(args.warmup):
+        oracle_step(burst, cfg, pool)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(burst, cfg, pool)
+    dt = (time.perf_counter() - t0) / args.steps
+    if pool is not None:
+        pool.close()
+    value = scaling / dt
+    sample = ("%d-frame %dx%d crop of the workload per step (same generator and config), comp frames spread over %d "
+              "processes; value = sample output MPix x (%d/%d frames) / seconds" % (n_frames, crop, crop, nproc, n_frames, wl["n"]))
+    line = {"impl": "reference", "metric": "output MPix/s (20x12MP->48MP burst)", "value": value, "unit": "MPix/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64 mixed (as the reference)",
+            "data": "synthetic", "config": {"workload": wl_name, **wl},
+            "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": nproc, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_cuda_arm(args, wl, wl_name):
+    import torch
+    import torch.distributed as dist
+    from handheld_super_resolution import _lib, super_resolution as SR
+    from handheld_super_resolution.distributed import main_sharded
+    from handheld_super_resolution.synthetic import synth_burst
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, H, W, scale = wl["n"], wl["H"], wl["W"], wl["scale"]
+    cfg = make_config(scale, H, W)
+    hs, ws = round(scale * H), round(scale * W)
+
+    burst_dev, _ = synth_burst(n, H, W, seed=0, device="cuda", as_numpy=False)      # same burst on every rank
+    burst_host = torch.empty((n, H, W), dtype=torch.float32).pin_memory()
+    burst_host.copy_(burst_dev)
+    out_host = torch.empty((hs, ws, 3), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    # per-launch timing of the dominant kernel (merge accumulate) with CUDA events on the launching stream
+    merge_events = []
+    orig_merge = SR.merge
+
+    def timed_merge(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_merge(*a, **k)
+        e1.record()
+        merge_events.append((e0, e1))
+    SR.merge = timed_merge
+
+    def step_resident():
+        out, _ = main_sharded(burst_dev[0], burst_dev[1:], cfg)
+        return out
+
+    def step_e2e():
+        out, _ = main_sharded(burst_host[0], burst_host[1:], cfg)
+        if rank == 0:
+            out_host.copy_(out, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps, t0, t1
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    merge_events.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    ms_res, t0, t1 = timed(step_resident, args.steps)
+    launches = (_lib.launch_count - launches0)
+    merge_ms = [a.elapsed_time(b) for a, b in merge_events]
+    merge_events.clear()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, t2 = timed(step_e2e, args.steps)
+    clocks = sampler.stop(t0, t2) if rank == 0 else None
+    SR.merge = orig_merge
+
+    if rank == 0:
+        out_mpix = hs * ws / 1e6
+        peak, peak_src = measured_peak_gbs()
+        ny, nx = -(-H // 32), -(-W // 32)
+        alg = merge_algorithmic_bytes(H, W, scale, ny, nx)
+        avg_merge_ms = float(np.mean(merge_ms)) if merge_ms else float("nan")
+        achieved = alg / (avg_merge_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "merge_traffic_bytes.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(wl_name)
+        line = {
+            "metric": "output MPix/s (20x12MP->48MP burst)" if wl_name == "20x12MP_s2" else "output MPix/s",
+            "value": out_mpix / (ms_res * 1e-3), "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (f64 sub-pixel positions)", "data": "synthetic",
+            "config": {"workload": wl_name, **wl, "tile_size": 32, "parallelism": "frames sharded over %d GPU(s), one NCCL sum" % world,
+                       "l2": "inputs per step (%.0f MB burst + %.0f MB accumulators) exceed the 126 MB L2; no flush needed"
+                             % (n * H * W * 4 / 1e6, hs * ws * 24 / 1e6)},
+            "e2e": {"value": out_mpix / (ms_e2e * 1e-3), "unit": "MPix/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(n * H * W * 4), "d2h_bytes_per_step": int(hs * ws * 3 * 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "accumulate_kernel (merge, one comp frame per launch)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_merge_ms,
+                         "launches_timed": len(merge_ms)},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(wl):
+    """The oracle port timed on this box's host cores on a bounded sample (single process: `cores` = 1)."""
+    burst, cfg, scaling = cpu_sample(wl, 3, 704, 1)
+    t0 = time.perf_counter()
+    oracle_step(burst, cfg, None)
+    dt = time.perf_counter() - t0
+    return {"value": scaling / dt, "unit": "MPix/s", "cores": 1, "kind": "port", "seconds": dt,
+            "sample": "3-frame 704x704 crop of the workload, NumPy oracle in one process; value = sample output MPix x "
+                      "(3/%d frames) / seconds (work ~ pixels x frames)" % wl["n"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="20x12MP_s2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl, args.workload)
+    else:
+        run_cuda_arm(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    main()

@@ -100,19 +100,18 @@ __global__ void upscale_flow_kernel(const float2 *__restrict__ in, int ny_in, in
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ ref, int ref_w, const float *__restrict__ mov,
                                                     int mov_h, int mov_w, float2 *__restrict__ flow, int nx, int ts, int r) {
-    extern __shared__ float bsm[];
+    extern __shared__ double bsm[];   // tile and window are staged as float64: the inner loop is 2 DFMA per sample
     const int tx = blockIdx.x, ty = blockIdx.y;
     const int sw = ts + 2 * r, n = 2 * r + 1;
-    float *s_ref = bsm, *s_win = bsm + ts * ts;
-    double *s_err = reinterpret_cast<double *>(bsm + ts * ts + ((sw * sw + 1) & ~1));
+    double *s_ref = bsm, *s_win = bsm + ts * ts, *s_err = bsm + ts * ts + sw * sw;
     const float2 f = flow[(size_t)ty * nx + tx];
     const int fx = (int)rintf(f.x), fy = (int)rintf(f.y);                       // flow.round(), :352
     for (int p = threadIdx.x; p < ts * ts; p += blockDim.x)
-        s_ref[p] = __ldg(ref + (size_t)(ty * ts + p / ts) * ref_w + tx * ts + p % ts);
+        s_ref[p] = -2.0 * (double)__ldg(ref + (size_t)(ty * ts + p / ts) * ref_w + tx * ts + p % ts);
     for (int p = threadIdx.x; p < sw * sw; p += blockDim.x) {
         const int yy = min(max(ty * ts + fy - r + p / sw, 0), mov_h - 1);       // clamp, :368-369
         const int xx = min(max(tx * ts + fx - r + p % sw, 0), mov_w - 1);
-        s_win[p] = __ldg(mov + (size_t)yy * mov_w + xx);
+        s_win[p] = (double)__ldg(mov + (size_t)yy * mov_w + xx);
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -121,8 +120,8 @@ __global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ re
         double e = 0.0;
         for (int p = lane; p < ts * ts; p += 32) {
             const int y = p / ts, x = p % ts;
-            const double m = (double)s_win[(y + v) * sw + x + u];
-            e += m * m - 2.0 * (double)s_ref[p] * m;
+            const double m = s_win[(y + v) * sw + x + u];
+            e = fma(m, m + s_ref[p], e);                                         // m^2 - 2 ref m
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
@@ -276,7 +275,7 @@ extern "C" int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const f
     HHSR_REQUIRE(radius >= 0 && radius <= 8, "search radius must be in [0, 8]");
     HHSR_REQUIRE(ny * ts <= ref_h && nx * ts <= ref_w, "tile grid exceeds the reference level");
     const int sw = ts + 2 * radius, n = 2 * radius + 1;
-    const size_t smem = (size_t)(ts * ts + ((sw * sw + 1) & ~1)) * sizeof(float) + (size_t)n * n * sizeof(double);
+    const size_t smem = (size_t)(ts * ts + sw * sw + n * n) * sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(bm_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(nx, ny);
     bm_l2_kernel<<<grid, ts >= 16 ? 256 : 64, smem, (cudaStream_t)stream>>>(ref, ref_w, mov, mov_h, mov_w,

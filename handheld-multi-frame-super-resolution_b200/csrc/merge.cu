@@ -27,34 +27,72 @@ struct MergeBatch {
 };
 struct MergeGeom {
     int H, W, nx, ts, ch, cw, Hs, Ws, cfa;
-    double scale;
+    double scale, inv_scale;
+    bool pow2;   // scale is a power of two: x / scale == x * (1/scale) exactly
 };
+
+static MergeGeom make_geom(int H, int W, int nx, int ts, int Hs, int Ws, const int *cfa, double scale) {
+    int e = 0;
+    const bool pow2 = std::frexp(scale, &e) == 0.5;
+    return MergeGeom{H, W, nx, ts, H / 2, W / 2, Hs, Ws, pack_cfa(cfa), scale, 1.0 / scale, pow2};
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// (hr + 0.5) / scale exactly as the reference forms it in float64 (merge.py:319-320).  For power-of-two scales the
+// multiplication by the (exact) reciprocal is the same correctly-rounded result and skips the fp64 division.
+__device__ __forceinline__ double lr_coord(int hr, double scale, double inv_scale, bool pow2) {
+    const double a = (double)hr + 0.5;
+    return pow2 ? a * inv_scale : a / scale;
+}
+
+// Split m = lr + flow (float64, merge.py:339-340) into integer part and float32 fraction; false if m leaves
+// [0, n) (merge.py:343-345).
+__device__ __forceinline__ bool split_pos(double lr, float flow, int n, int &c, float &t) {
+    const double m = lr + (double)flow;
+    if (!(m >= 0.0 && m < (double)n)) return false;
+    c = (int)m;
+    t = (float)(m - (double)c);
+    return true;
+}
+
+// Bilinear lookup coordinates of the covariance map at k = m/2 - 0.5 (merge.py:350-363, trunc + signed modf),
+// derived exactly from m = c + t:  c odd -> k = (c-1)/2 + t/2;  c even -> k = c/2 - 1 + (0.5 + t/2);
+// c == 0 -> k in [-0.5, 0): index 0 with a negative fraction (the reference extrapolates there).
+__device__ __forceinline__ void cov_coord(int c, float t, int n, int &i0, int &i1, float &fr) {
+    if (c & 1) {
+        i0 = c >> 1;
+        fr = 0.5f * t;
+    } else if (c > 0) {
+        i0 = (c >> 1) - 1;
+        fr = 0.5f + 0.5f * t;
+    } else {
+        i0 = 0;
+        fr = 0.5f * t - 0.5f;
+    }
+    i1 = min(i0 + 1, n - 1);
+}
 
 // Contribution of one comp frame to one HR pixel.  v/a: partial sums per tap parity relative to the centre tap
 // (row parity, col parity) -> the CFA channel of each partial is resolved once at the end.
 template <bool ISO>
-__device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom &g, double lr_x, double lr_y,
-                                            float (&val)[3], float (&acc)[3]) {
-    const int px = (int)floor(lr_x / g.ts), py = (int)floor(lr_y / g.ts);       // merge.py:322-323
-    const float2 fl = __ldg(reinterpret_cast<const float2 *>(f.flow) + py * g.nx + px);
-    const int i_r = min((int)lr_y, g.H - 1), j_r = min((int)lr_x, g.W - 1);     // merge.py:335-336
-    const float local_r = __ldg(f.r + (size_t)i_r * g.W + j_r);
-    const double mx = lr_x + (double)fl.x, my = lr_y + (double)fl.y;             // merge.py:339-340
-    if (!(mx >= 0.0 && mx < (double)g.W && my >= 0.0 && my < (double)g.H)) return;   // :343-345
-    const int cj = (int)mx, ci = (int)my;
-    const float tx = (float)(mx - (double)cj), ty = (float)(my - (double)ci);
-    // quadratic form pre-scaled by -0.5*log2(e): w = exp(-z/2) = 2^(qxx dx^2 + 2 qxy dx dy + qyy dy^2)
+__device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom &g, int cj, float tx, int ci, float ty,
+                                            float local_r, float (&val)[3], float (&acc)[3]) {
+    // quadratic form pre-scaled by -0.5*log2(e): w = exp(-z/2) = 2^(qxx dx^2 + qxy dx dy + qyy dy^2)
     const float kS = -0.72134752044448170368f;
     float qxx, qxy, qyy;
     if (ISO) {
         qxx = qyy = 2.0f * kS;   // z = 2 (dx^2 + dy^2), merge.py:419
         qxy = 0.0f;
     } else {
-        const double kj = mx * 0.5 - 0.5, ki = my * 0.5 - 0.5;                   // merge.py:350-351 (bayer)
-        const double tkj = trunc(kj), tki = trunc(ki);
-        const float frx = (float)(kj - tkj), fry = (float)(ki - tki);           // signed modf, :357-358
-        const int fx0 = max((int)tkj, 0), fy0 = max((int)tki, 0);
-        const int cx1 = min(fx0 + 1, g.cw - 1), cy1 = min(fy0 + 1, g.ch - 1);
+        int fx0, cx1, fy0, cy1;
+        float frx, fry;
+        cov_coord(cj, tx, g.cw, fx0, cx1, frx);
+        cov_coord(ci, ty, g.ch, fy0, cy1, fry);
         const float4 *c4 = reinterpret_cast<const float4 *>(f.covs);
         const float4 tr = __ldg(c4 + (size_t)fy0 * g.cw + fx0), tl = __ldg(c4 + (size_t)fy0 * g.cw + cx1);
         const float4 br = __ldg(c4 + (size_t)cy1 * g.cw + fx0), bl = __ldg(c4 + (size_t)cy1 * g.cw + cx1);
@@ -64,7 +102,7 @@ __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom
         const float cxx = top_xx + fry * (bot_xx - top_xx);
         const float cxy = top_xy + fry * (bot_xy - top_xy);
         const float cyy = top_yy + fry * (bot_yy - top_yy);
-        const float inv_det = kS / (cxx * cyy - cxy * cxy);                      // merge.py:391-396
+        const float inv_det = __fdividef(kS, cxx * cyy - cxy * cxy);             // merge.py:391-396
         qxx = inv_det * cyy;
         qxy = -2.0f * inv_det * cxy;
         qyy = inv_det * cxx;
@@ -75,6 +113,7 @@ __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom
         const int i = ci + di;
         if (i < 0 || i >= g.H) continue;
         const float dy = (float)di + 0.5f - ty;                                   // i - (lr_mov_y - 0.5)
+        const float qy = qyy * dy * dy, qm = qxy * dy;
         const float *row = f.raw + (size_t)i * g.W;
 #pragma unroll
         for (int dj = -1; dj <= 1; ++dj) {
@@ -82,9 +121,9 @@ __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom
             if (j < 0 || j >= g.W) continue;
             const float c = __ldg(row + j);
             const float dx = (float)dj + 0.5f - tx;
-            float z = qxx * dx * dx + qxy * dx * dy + qyy * dy * dy;
+            float z = (qxx * dx + qm) * dx + qy;
             z = fminf(0.0f, z);               // == -0.5*log2e*max(0, z_ref); NaN -> 0
-            const float wr = exp2f(z) * local_r;
+            const float wr = ex2_approx(z) * local_r;
             v[di & 1][dj & 1] += wr * c;
             a[di & 1][dj & 1] += wr;
         }
@@ -103,8 +142,8 @@ __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom
 }
 
 template <bool ISO, int VEC>
-__global__ void __launch_bounds__(256) accumulate_kernel(MergeBatch b, MergeGeom g, float *__restrict__ num,
-                                                         float *__restrict__ den) {
+__global__ void __launch_bounds__(256, 3) accumulate_kernel(MergeBatch b, MergeGeom g, float *__restrict__ num,
+                                                            float *__restrict__ den) {
     const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (hr_i >= g.Hs || j0 >= g.Ws) return;
@@ -127,14 +166,25 @@ __global__ void __launch_bounds__(256) accumulate_kernel(MergeBatch b, MergeGeom
             d[q] = ok ? den[base + q] : 0.f;
         }
     }
-    const double lr_y = ((double)hr_i + 0.5) / g.scale;                         // merge.py:319-320
+    const double lr_y = lr_coord(hr_i, g.scale, g.inv_scale, g.pow2);           // merge.py:319-320
+    const int ily = (int)lr_y;
+    const int py = ily / g.ts, i_r = min(ily, g.H - 1);                          // merge.py:322-323, 335-336
     for (int k = 0; k < b.K; ++k) {
+        const MergeFrame &f = b.f[k];
+        const float2 *flow_row = reinterpret_cast<const float2 *>(f.flow) + (size_t)py * g.nx;
+        const float *r_row = f.r + (size_t)i_r * g.W;
 #pragma unroll
         for (int p = 0; p < VEC; ++p) {
             if (j0 + p >= g.Ws) break;
+            const double lr_x = lr_coord(j0 + p, g.scale, g.inv_scale, g.pow2);
+            const int ilx = (int)lr_x;
+            const float2 fl = __ldg(flow_row + ilx / g.ts);
+            int cj, ci;
+            float tx, ty;
+            if (!split_pos(lr_x, fl.x, g.W, cj, tx) || !split_pos(lr_y, fl.y, g.H, ci, ty)) continue;
+            const float local_r = __ldg(r_row + min(ilx, g.W - 1));
             float val[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
-            const double lr_x = ((double)(j0 + p) + 0.5) / g.scale;
-            merge_pixel<ISO>(b.f[k], g, lr_x, lr_y, val, acc);
+            merge_pixel<ISO>(f, g, cj, tx, ci, ty, local_r, val, acc);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 n[p * 3 + c] += val[c];
@@ -306,7 +356,7 @@ extern "C" int hhsr_merge_accumulate_batch(const float *const *raws, const float
     HHSR_REQUIRE(iso || covs, "covs required for the steerable kernel");
     if (int e = check_merge_args(raws[0], num, den, H, W, Hs, Ws, scale, cfa_host)) return e;
     HHSR_REQUIRE(ts > 0 && ny * ts >= H && nx * ts >= W, "flow grid does not cover the frame");
-    MergeGeom g{H, W, nx, ts, H / 2, W / 2, Hs, Ws, pack_cfa(cfa_host), scale};
+    MergeGeom g = make_geom(H, W, nx, ts, Hs, Ws, cfa_host, scale);
     for (int k0 = 0; k0 < K; k0 += kMaxBatch) {
         MergeBatch b;
         b.K = (K - k0 < kMaxBatch) ? K - k0 : kMaxBatch;
@@ -334,7 +384,7 @@ extern "C" int hhsr_merge_ref(const float *raw, int H, int W, const float *covs,
     if (int e = check_merge_args(raw, num, den, H, W, Hs, Ws, scale, cfa_host)) return e;
     HHSR_REQUIRE(iso || (covs && (uintptr_t)covs % 16 == 0), "covs required (16-byte aligned) for the steerable kernel");
     HHSR_REQUIRE(acc_rob == nullptr || rad_max >= 0, "rad_max must be >= 0");
-    MergeGeom g{H, W, 0, 0, H / 2, W / 2, Hs, Ws, pack_cfa(cfa_host), scale};
+    MergeGeom g = make_geom(H, W, 0, 1, Hs, Ws, cfa_host, scale);
     dim3 block(32, 8), grid(ceil_div(Ws, 32), ceil_div(Hs, 8));
     if (iso)
         accumulate_ref_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(raw, covs, g, num, den, acc_rob, max_frame_count,

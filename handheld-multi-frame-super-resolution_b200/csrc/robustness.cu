@@ -110,6 +110,43 @@ __device__ __forceinline__ bool dodgson_sample(const float *__restrict__ lr, int
     return true;
 }
 
+// Same sampler for the per-frame hot kernel, in float32 with an exact integer/fraction split of the position:
+// y + 0.5 + f = T + u with T = y + trunc(f) (integer), u = 0.5 + frac(f) (float32, exact to 1 ulp), hence
+// ly = (T + u)/2 - 0.5 = (T >> 1) + v, v = 0.5 (T & 1) + u/2 - 0.5 in (-1, 1): tap offsets and Dodgson weights are
+// formed from v, so the float32 result agrees with the reference's float64 weights to float32 rounding (positions
+// of several thousand pixels would otherwise cost 1e-4 px).
+struct Axis {
+    int i[3];      // clamped tap indices
+    float w[3];    // Dodgson weights
+    bool ok;
+};
+__device__ __forceinline__ float dodgson_f(float t) {
+    const float a = fabsf(t);
+    if (a <= 0.5f) return -2.0f * a * a + 1.0f;
+    if (a <= 1.5f) return a * a - 2.5f * a + 1.5f;
+    return 0.0f;
+}
+__device__ __forceinline__ Axis dodgson_axis(int y, float f, int n) {
+    Axis A;
+    const float tf = truncf(f);
+    const int T = y + (int)tf;
+    const float u = 0.5f + (f - tf);
+    const int base = T >> 1;                                  // arithmetic shift == floor(T/2)
+    const float v = 0.5f * (float)(T & 1) + 0.5f * u - 0.5f;   // ly = base + v
+    const int fl = base + (int)floorf(v);
+    A.ok = (fl >= 0) && (fl < n);                             // 0 <= ly < n  (robustness.py:383-384)
+    float rv = rintf(v);
+    int c = base + (int)rv;
+    if (fabsf(v - rv) == 0.5f && (c & 1)) c += (v > rv) ? 1 : -1;   // round half to even on ly, not on v
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int q = min(max(c + k - 1, 0), n - 1);
+        A.i[k] = q;
+        A.w[k] = dodgson_f((float)(q - base) - v);
+    }
+    return A;
+}
+
 __global__ void __launch_bounds__(RBX *RBY) upscale_warp_kernel(const float *__restrict__ lr, int h, int w,
                                                                 const float *__restrict__ flow, int nx, int ts,
                                                                 float *__restrict__ hr) {
@@ -133,6 +170,23 @@ struct RobParams {
     int n_curve;
 };
 
+// flow irregularity of tile (py, px): s1 if the range of the flow over the 3x3 tile neighbourhood exceeds Mt
+// (robustness.py:569-611)
+__device__ __forceinline__ float tile_S(const float2 *__restrict__ fl, int py, int px, int ny, int nx, const RobParams &p) {
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+#pragma unroll
+    for (int i = -1; i <= 1; ++i)
+#pragma unroll
+        for (int j = -1; j <= 1; ++j) {
+            const int yy = py + i, xx = px + j;
+            if (yy < 0 || yy >= ny || xx < 0 || xx >= nx) continue;
+            const float2 q = __ldg(fl + (size_t)yy * nx + xx);
+            mxx = fmaxf(mxx, q.x), mxy = fmaxf(mxy, q.y), mnx = fminf(mnx, q.x), mny = fminf(mny, q.y);
+        }
+    const float d0 = mxx - mnx, d1 = mxy - mny;
+    return ((double)(d0 * d0 + d1 * d1) > p.Mt * p.Mt) ? (float)p.s1 : (float)p.s2;
+}
+
 __global__ void __launch_bounds__(RBX *RBY) robustness_kernel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
                                                               const float *__restrict__ ref_vars, int H, int W,
                                                               const float *__restrict__ flow, int ny, int nx, int ts,
@@ -140,46 +194,64 @@ __global__ void __launch_bounds__(RBX *RBY) robustness_kernel(const float *__res
                                                               const double *__restrict__ diff_curve, RobParams p,
                                                               float *__restrict__ R) {
     const int x = blockIdx.x * RBX + threadIdx.x, y = blockIdx.y * RBY + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const int py = y / ts, px = x / ts;
     const float2 *fl = reinterpret_cast<const float2 *>(flow);
-    const float2 f = __ldg(fl + (size_t)py * nx + px);
-    float cm[3];
-    const bool ok = dodgson_sample(comp_lr, H / 2, W / 2, y, x, f.x, f.y, cm);
-    const size_t plane = (size_t)H * W, o = (size_t)y * W + x;
+    // a 32x8 block lies inside one flow tile when ts is a multiple of 32: flow and S are then block-uniform
+    __shared__ float s_S;
+    __shared__ float2 s_f;
+    const bool uniform = (ts % RBX) == 0;
+    if (uniform) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const int py = (blockIdx.y * RBY) / ts, px = (blockIdx.x * RBX) / ts;
+            s_f = __ldg(fl + (size_t)py * nx + px);
+            s_S = tile_S(fl, py, px, ny, nx, p);
+        }
+        __syncthreads();
+    }
+    if (x >= W || y >= H) return;
+    float2 f;
+    float S;
+    if (uniform) {
+        f = s_f, S = s_S;
+    } else {
+        const int py = y / ts, px = x / ts;
+        f = __ldg(fl + (size_t)py * nx + px);
+        S = tile_S(fl, py, px, ny, nx, p);
+    }
+    const int h = H / 2, w = W / 2;
+    const size_t plane = (size_t)H * W, lplane = (size_t)h * w, o = (size_t)y * W + x;
+    const Axis ay = dodgson_axis(y, f.y, h), ax = dodgson_axis(x, f.x, w);
     float out = 0.f;   // any non-finite statistic ends as clamp(NaN) = 0 in the reference
     const float rm0 = __ldg(ref_means + o);
-    if (ok && isfinite(rm0)) {
-        double sigma_sq = 0.0, d_sq = 0.0;
+    if (ay.ok && ax.ok && isfinite(rm0)) {
+        float buf[3] = {0.f, 0.f, 0.f}, wacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float *row = comp_lr + (size_t)ay.i[i] * w;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float wgt = ay.w[i] * ax.w[j];
+                const float *q = row + ax.i[j];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) buf[c] = fmaf(__ldg(q + c * lplane), wgt, buf[c]);
+                wacc += wgt;
+            }
+        }
+        const float inv_w = 1.0f / wacc;
+        float sigma_sq = 0.f, d_sq = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float brightness = c == 0 ? rm0 : __ldg(ref_means + o + c * plane);
             long long id = llrint(1000.0 * (double)brightness);                 // robustness.py:519
             id = id < 0 ? 0 : (id >= p.n_curve ? p.n_curve - 1 : id);
-            const double d_t = __ldg(diff_curve + id), sigma_t = __ldg(std_curve + id);
+            const float d_t = (float)__ldg(diff_curve + id), sigma_t = (float)__ldg(std_curve + id);
             const float sigma_p_sq = __ldg(ref_vars + o + c * plane);
-            const double st2 = sigma_t * sigma_t;
-            sigma_sq += (st2 > (double)sigma_p_sq) ? st2 : (double)sigma_p_sq;  // max(sigma_p_sq, sigma_t^2)
-            const float d_p = fabsf(brightness - cm[c]);                        // :462
-            const float d_p_sq = __fmul_rn(d_p, d_p);
-            const double shrink = (double)d_p_sq / ((double)d_p_sq + d_t * d_t);
-            d_sq += (double)d_p_sq * shrink * shrink;
+            sigma_sq += fmaxf(sigma_p_sq, sigma_t * sigma_t);                   // :524
+            const float d_p = fabsf(brightness - buf[c] * inv_w);               // :462
+            const float d_p_sq = d_p * d_p;
+            const float shrink = d_p_sq / (d_p_sq + d_t * d_t);
+            d_sq += d_p_sq * shrink * shrink;
         }
-        const float sigma_f = (float)sigma_sq, d_f = (float)d_sq;               // stored as float32 arrays
-        // flow irregularity, robustness.py:569-611
-        float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-#pragma unroll
-        for (int i = -1; i <= 1; ++i)
-#pragma unroll
-            for (int j = -1; j <= 1; ++j) {
-                const int yy = py + i, xx = px + j;
-                if (yy < 0 || yy >= ny || xx < 0 || xx >= nx) continue;
-                const float2 q = __ldg(fl + (size_t)yy * nx + xx);
-                mxx = fmaxf(mxx, q.x), mxy = fmaxf(mxy, q.y), mnx = fminf(mnx, q.x), mny = fminf(mny, q.y);
-            }
-        const float d0 = mxx - mnx, d1 = mxy - mny;
-        const float S = ((double)(d0 * d0 + d1 * d1) > p.Mt * p.Mt) ? (float)p.s1 : (float)p.s2;
-        const float e = expf(-d_f / sigma_f);                                    // math.exp(float32), :638
+        const float e = expf(-d_sq / sigma_sq);                                  // math.exp(float32), :638
         double v = (double)(S * e) - p.t;
         v = (v > 0.0) ? v : 0.0;
         v = (v < 1.0) ? v : 1.0;
