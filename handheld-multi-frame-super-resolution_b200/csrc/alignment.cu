@@ -98,30 +98,45 @@ __global__ void upscale_flow_kernel(const float2 *__restrict__ in, int ny_in, in
 // L2 block matching.  E(v,u) = sum m^2 - 2 sum ref*m, accumulated in float64 so the argmin is the exact one
 // (the reference obtains the same quantity through float32 FFTs; only exact/near ties can differ).
 // ---------------------------------------------------------------------------------------------------------
+template <int TS>
 __global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ ref, int ref_w, const float *__restrict__ mov,
-                                                    int mov_h, int mov_w, float2 *__restrict__ flow, int nx, int ts, int r) {
-    extern __shared__ double bsm[];   // tile and window are staged as float64: the inner loop is 2 DFMA per sample
+                                                    int mov_h, int mov_w, float2 *__restrict__ flow, int nx, int r) {
+    extern __shared__ double bsm[];   // tile and window are staged as float64: the inner loop is LDS.64 + DFMA
+    constexpr int NT = TS >= 16 ? 256 : 64;
+    constexpr int CPL = TS > 32 ? TS / 32 : 1;          // columns per lane
+    constexpr int LPR = TS >= 32 ? 32 : TS;             // lanes per row
+    constexpr int RPP = 32 / LPR;                       // rows per pass of a warp
     const int tx = blockIdx.x, ty = blockIdx.y;
-    const int sw = ts + 2 * r, n = 2 * r + 1;
-    double *s_ref = bsm, *s_win = bsm + ts * ts, *s_err = bsm + ts * ts + sw * sw;
+    const int sw = TS + 2 * r, n = 2 * r + 1;
+    double *s_ref = bsm, *s_win = bsm + TS * TS, *s_err = bsm + TS * TS + sw * sw;
     const float2 f = flow[(size_t)ty * nx + tx];
     const int fx = (int)rintf(f.x), fy = (int)rintf(f.y);                       // flow.round(), :352
-    for (int p = threadIdx.x; p < ts * ts; p += blockDim.x)
-        s_ref[p] = -2.0 * (double)__ldg(ref + (size_t)(ty * ts + p / ts) * ref_w + tx * ts + p % ts);
-    for (int p = threadIdx.x; p < sw * sw; p += blockDim.x) {
-        const int yy = min(max(ty * ts + fy - r + p / sw, 0), mov_h - 1);       // clamp, :368-369
-        const int xx = min(max(tx * ts + fx - r + p % sw, 0), mov_w - 1);
-        s_win[p] = (double)__ldg(mov + (size_t)yy * mov_w + xx);
+    for (int p = threadIdx.x; p < TS * TS; p += NT)
+        s_ref[p] = -2.0 * (double)__ldg(ref + (size_t)(ty * TS + p / TS) * ref_w + tx * TS + p % TS);
+    for (int yy0 = threadIdx.x / 32; yy0 < sw; yy0 += NT / 32) {               // one warp per window row
+        const int yy = min(max(ty * TS + fy - r + yy0, 0), mov_h - 1);          // clamp, :368-369
+        for (int xx0 = threadIdx.x & 31; xx0 < sw; xx0 += 32) {
+            const int xx = min(max(tx * TS + fx - r + xx0, 0), mov_w - 1);
+            s_win[yy0 * sw + xx0] = (double)__ldg(mov + (size_t)yy * mov_w + xx);
+        }
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int s = warp; s < n * n; s += nwarps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (lane % LPR) * CPL, ly0 = lane / LPR;
+    for (int s = warp; s < n * n; s += NT / 32) {
         const int v = s / n, u = s % n;
         double e = 0.0;
-        for (int p = lane; p < ts * ts; p += 32) {
-            const int y = p / ts, x = p % ts;
-            const double m = s_win[(y + v) * sw + x + u];
-            e = fma(m, m + s_ref[p], e);                                         // m^2 - 2 ref m
+        const double *wp = s_win + (ly0 + v) * sw + lx + u;
+        const double *rp = s_ref + ly0 * TS + lx;
+#pragma unroll 4
+        for (int y = 0; y < TS; y += RPP) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const double m = wp[c];
+                e = fma(m, m + rp[c], e);                                        // m^2 - 2 ref m
+            }
+            wp += RPP * sw;
+            rp += RPP * TS;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
@@ -276,10 +291,21 @@ extern "C" int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const f
     HHSR_REQUIRE(ny * ts <= ref_h && nx * ts <= ref_w, "tile grid exceeds the reference level");
     const int sw = ts + 2 * radius, n = 2 * radius + 1;
     const size_t smem = (size_t)(ts * ts + sw * sw + n * n) * sizeof(double);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(bm_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(nx, ny);
-    bm_l2_kernel<<<grid, ts >= 16 ? 256 : 64, smem, (cudaStream_t)stream>>>(ref, ref_w, mov, mov_h, mov_w,
-                                                                           reinterpret_cast<float2 *>(flow), nx, ts, radius);
+    cudaStream_t st = (cudaStream_t)stream;
+    float2 *F2 = reinterpret_cast<float2 *>(flow);
+#define HHSR_BM(TS, NT)                                                                                      \
+    do {                                                                                                     \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(bm_l2_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        bm_l2_kernel<TS><<<grid, NT, smem, st>>>(ref, ref_w, mov, mov_h, mov_w, F2, nx, radius);              \
+    } while (0)
+    switch (ts) {
+        case 8: HHSR_BM(8, 64); break;
+        case 16: HHSR_BM(16, 256); break;
+        case 32: HHSR_BM(32, 256); break;
+        default: HHSR_BM(64, 256); break;
+    }
+#undef HHSR_BM
     return launch_status("bm_l2_search");
 }
 

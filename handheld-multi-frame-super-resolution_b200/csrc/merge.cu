@@ -15,6 +15,15 @@
 // burst and keeps the reference's float64 arithmetic literally.
 #include "common.cuh"
 
+// tuning knobs (see profiles/): resident CTAs per SM the register allocator must allow, and whether a thread keeps
+// the four covariance quads of its previous pixel in registers
+#ifndef HHSR_MERGE_MINBLOCKS
+#define HHSR_MERGE_MINBLOCKS 5
+#endif
+#ifndef HHSR_MERGE_REUSE_QUADS
+#define HHSR_MERGE_REUSE_QUADS 0
+#endif
+
 namespace hhsr {
 
 struct MergeFrame {
@@ -25,16 +34,45 @@ struct MergeBatch {
     MergeFrame f[kMaxBatch];
     int K;
 };
-struct MergeGeom {
-    int H, W, nx, ts, ch, cw, Hs, Ws, cfa;
-    double scale, inv_scale;
-    bool pow2;   // scale is a power of two: x / scale == x * (1/scale) exactly
+// CFA descriptor: packed 2x2 channel ids + whether it is a Bayer pattern (one channel twice, on a diagonal).
+struct CfaInfo {
+    int packed;
+    int bayer;       // 1: the fast channel resolve is valid
+    int dup;         // the duplicated channel (green)
+    int dup_main;    // 1 if the duplicated channel sits on the main diagonal (0,0),(1,1)
+    int lo;          // the smaller of the two single channels
 };
+struct MergeGeom {
+    int H, W, nx, ts, ch, cw, Hs, Ws;
+    CfaInfo cfa;
+    double scale, inv_scale;
+    bool pow2;      // scale is a power of two: x / scale == x * (1/scale) exactly
+    int ts_shift;   // log2(ts) when ts is a power of two, else -1
+};
+
+__device__ __forceinline__ int tile_of(int i, const MergeGeom &g) { return g.ts_shift >= 0 ? (i >> g.ts_shift) : (i / g.ts); }
+
+static CfaInfo make_cfa(const int *c) {
+    CfaInfo f{pack_cfa(c), 0, 0, 0, 0};
+    int dup = -1, main_diag = 0;
+    if (c[0] == c[3] && c[1] != c[2]) dup = c[0], main_diag = 1;
+    if (c[1] == c[2] && c[0] != c[3]) dup = c[1], main_diag = 0;
+    if (dup >= 0) {
+        const int s0 = main_diag ? c[1] : c[0], s1 = main_diag ? c[2] : c[3];
+        if (s0 != dup && s1 != dup && s0 != s1) {
+            f.bayer = 1, f.dup = dup, f.dup_main = main_diag, f.lo = s0 < s1 ? s0 : s1;
+        }
+    }
+    return f;
+}
 
 static MergeGeom make_geom(int H, int W, int nx, int ts, int Hs, int Ws, const int *cfa, double scale) {
     int e = 0;
     const bool pow2 = std::frexp(scale, &e) == 0.5;
-    return MergeGeom{H, W, nx, ts, H / 2, W / 2, Hs, Ws, pack_cfa(cfa), scale, 1.0 / scale, pow2};
+    int shift = -1;
+    for (int k = 0; k < 16; ++k)
+        if ((1 << k) == ts) shift = k;
+    return MergeGeom{H, W, nx, ts, H / 2, W / 2, Hs, Ws, make_cfa(cfa), scale, 1.0 / scale, pow2, shift};
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -77,13 +115,79 @@ __device__ __forceinline__ void cov_coord(int c, float t, int n, int &i0, int &i
     i1 = min(i0 + 1, n - 1);
 }
 
-// Contribution of one comp frame to one HR pixel.  v/a: partial sums per tap parity relative to the centre tap
-// (row parity, col parity) -> the CFA channel of each partial is resolved once at the end.
-template <bool ISO>
+// 3x3 taps around (ci, cj).  v/a: partial sums per tap parity RELATIVE to the centre tap (row parity, col parity),
+// so the accumulation indices are compile-time; the CFA channel of each partial is resolved once at the end.
+// CHECK=false is the interior fast path (all 9 taps inside the frame, no per-tap tests).
+template <bool CHECK>
+__device__ __forceinline__ void merge_taps(const float *__restrict__ raw, int H, int W, int ci, int cj, float tx, float ty,
+                                           float qxx, float qxy, float qyy, float (&v)[2][2], float (&a)[2][2]) {
+    const float *pc = raw + ((unsigned)max(ci, 0) * (unsigned)W + (unsigned)max(cj, 0));
+#pragma unroll
+    for (int di = -1; di <= 1; ++di) {
+        if (CHECK && (ci + di < 0 || ci + di >= H)) continue;
+        const float dy = (float)di + 0.5f - ty;                                   // i - (lr_mov_y - 0.5)
+        const float qy = qyy * dy * dy, qm = qxy * dy;
+        const float *row = pc + di * W;
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) {
+            if (CHECK && (cj + dj < 0 || cj + dj >= W)) continue;
+            const float c = __ldg(row + dj);
+            const float dx = (float)dj + 0.5f - tx;
+            float z = (qxx * dx + qm) * dx + qy;
+            z = fminf(0.0f, z);               // == -0.5*log2e*max(0, z_ref); NaN -> 0 (SURVEY Q5)
+            const float w = ex2_approx(z);
+            v[di & 1][dj & 1] = fmaf(w, c, v[di & 1][dj & 1]);
+            a[di & 1][dj & 1] += w;
+        }
+    }
+}
+
+// Fold the four parity partials into the three colour channels, scaled by the robustness r:
+// out = r * sum (ACCUM: out += r * sum).  Bayer patterns take 7 selects; anything else the generic 12.
+template <bool ACCUM>
+__device__ __forceinline__ void resolve_channels(const CfaInfo &cf, int ci, int cj, float r, const float (&v)[2][2],
+                                                 float (&out)[3]) {
+    float ch[3];
+    if (cf.bayer) {
+        // rel main diagonal == abs main diagonal iff ci and cj have equal parity
+        const bool gm = ((cf.dup_main ^ ((ci ^ cj) & 1)) != 0);      // duplicated channel on the REL main diagonal
+        const float g = (gm ? v[0][0] : v[0][1]) + (gm ? v[1][1] : v[1][0]);
+        const float p = gm ? v[0][1] : v[0][0];                      // rel (0, gm) -> abs (ci, cj + gm)
+        const float q = gm ? v[1][0] : v[1][1];
+        const bool p_is_lo = (cfa_channel(cf.packed, ci, cj + (gm ? 1 : 0)) == cf.lo);
+        const float lo = p_is_lo ? p : q, hi = p_is_lo ? q : p;
+        if (cf.dup == 1) {                                           // RGGB / BGGR / GRBG / GBRG: green is channel 1
+            ch[0] = lo, ch[1] = g, ch[2] = hi;
+        } else {
+            ch[0] = (cf.dup == 0) ? g : (cf.lo == 0 ? lo : hi);
+            ch[1] = (cf.lo == 1) ? lo : hi;
+            ch[2] = (cf.dup == 2) ? g : (cf.lo == 2 ? lo : hi);
+        }
+    } else {
+        ch[0] = ch[1] = ch[2] = 0.f;
+#pragma unroll
+        for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+            for (int rx = 0; rx < 2; ++rx) {
+                const int chn = cfa_channel(cf.packed, ci + ry, cj + rx);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ch[k] += (chn == k) ? v[ry][rx] : 0.0f;
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] = ACCUM ? fmaf(r, ch[k], out[k]) : r * ch[k];
+}
+
+// Interpolated covariance -> pre-scaled inverse quadratic form.  w = exp(-z/2) = 2^(qxx dx^2 + qxy dx dy + qyy dy^2)
+struct CovQuads {
+    int fx0, fy0;
+    float4 tr, tl, br, bl;
+};
+
+template <bool ISO, bool ACCUM>
 __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom &g, int cj, float tx, int ci, float ty,
-                                            float local_r, float (&val)[3], float (&acc)[3]) {
-    // quadratic form pre-scaled by -0.5*log2(e): w = exp(-z/2) = 2^(qxx dx^2 + qxy dx dy + qyy dy^2)
-    const float kS = -0.72134752044448170368f;
+                                            float local_r, CovQuads &cq, float (&val)[3], float (&acc)[3]) {
+    const float kS = -0.72134752044448170368f;   // -0.5 * log2(e)
     float qxx, qxy, qyy;
     if (ISO) {
         qxx = qyy = 2.0f * kS;   // z = 2 (dx^2 + dy^2), merge.py:419
@@ -93,12 +197,15 @@ __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom
         float frx, fry;
         cov_coord(cj, tx, g.cw, fx0, cx1, frx);
         cov_coord(ci, ty, g.ch, fy0, cy1, fry);
-        const float4 *c4 = reinterpret_cast<const float4 *>(f.covs);
-        const float4 tr = __ldg(c4 + (size_t)fy0 * g.cw + fx0), tl = __ldg(c4 + (size_t)fy0 * g.cw + cx1);
-        const float4 br = __ldg(c4 + (size_t)cy1 * g.cw + fx0), bl = __ldg(c4 + (size_t)cy1 * g.cw + cx1);
-        const float top_xx = tr.x + frx * (tl.x - tr.x), bot_xx = br.x + frx * (bl.x - br.x);
-        const float top_xy = tr.y + frx * (tl.y - tr.y), bot_xy = br.y + frx * (bl.y - br.y);
-        const float top_yy = tr.w + frx * (tl.w - tr.w), bot_yy = br.w + frx * (bl.w - br.w);
+        if (!HHSR_MERGE_REUSE_QUADS || fx0 != cq.fx0 || fy0 != cq.fy0) {     // neighbouring HR pixels mostly share their four quads
+            const float4 *c4 = reinterpret_cast<const float4 *>(f.covs);
+            const float4 *r0 = c4 + (unsigned)fy0 * (unsigned)g.cw, *r1 = c4 + (unsigned)cy1 * (unsigned)g.cw;
+            cq.tr = __ldg(r0 + fx0), cq.tl = __ldg(r0 + cx1), cq.br = __ldg(r1 + fx0), cq.bl = __ldg(r1 + cx1);
+            cq.fx0 = fx0, cq.fy0 = fy0;
+        }
+        const float top_xx = cq.tr.x + frx * (cq.tl.x - cq.tr.x), bot_xx = cq.br.x + frx * (cq.bl.x - cq.br.x);
+        const float top_xy = cq.tr.y + frx * (cq.tl.y - cq.tr.y), bot_xy = cq.br.y + frx * (cq.bl.y - cq.br.y);
+        const float top_yy = cq.tr.w + frx * (cq.tl.w - cq.tr.w), bot_yy = cq.br.w + frx * (cq.bl.w - cq.br.w);
         const float cxx = top_xx + fry * (bot_xx - top_xx);
         const float cxy = top_xy + fry * (bot_xy - top_xy);
         const float cyy = top_yy + fry * (bot_yy - top_yy);
@@ -108,49 +215,116 @@ __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom
         qyy = inv_det * cxx;
     }
     float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, a[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-#pragma unroll
-    for (int di = -1; di <= 1; ++di) {
-        const int i = ci + di;
-        if (i < 0 || i >= g.H) continue;
-        const float dy = (float)di + 0.5f - ty;                                   // i - (lr_mov_y - 0.5)
-        const float qy = qyy * dy * dy, qm = qxy * dy;
-        const float *row = f.raw + (size_t)i * g.W;
-#pragma unroll
-        for (int dj = -1; dj <= 1; ++dj) {
-            const int j = cj + dj;
-            if (j < 0 || j >= g.W) continue;
-            const float c = __ldg(row + j);
-            const float dx = (float)dj + 0.5f - tx;
-            float z = (qxx * dx + qm) * dx + qy;
-            z = fminf(0.0f, z);               // == -0.5*log2e*max(0, z_ref); NaN -> 0 (SURVEY Q5)
-            const float wr = ex2_approx(z) * local_r;
-            v[di & 1][dj & 1] += wr * c;
-            a[di & 1][dj & 1] += wr;
-        }
-    }
-#pragma unroll
-    for (int ry = 0; ry < 2; ++ry)
-#pragma unroll
-        for (int rx = 0; rx < 2; ++rx) {
-            const int chn = cfa_channel(g.cfa, ci + ry, cj + rx);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                val[k] += (chn == k) ? v[ry][rx] : 0.0f;
-                acc[k] += (chn == k) ? a[ry][rx] : 0.0f;
-            }
-        }
+    if (ci >= 1 && ci <= g.H - 2 && cj >= 1 && cj <= g.W - 2)
+        merge_taps<false>(f.raw, g.H, g.W, ci, cj, tx, ty, qxx, qxy, qyy, v, a);
+    else
+        merge_taps<true>(f.raw, g.H, g.W, ci, cj, tx, ty, qxx, qxy, qyy, v, a);
+    // the reference multiplies every tap weight by r (merge.py:430-431); factored out here (float32 rounding level)
+    resolve_channels<ACCUM>(g.cfa, ci, cj, local_r, v, val);
+    resolve_channels<ACCUM>(g.cfa, ci, cj, local_r, a, acc);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// One thread = VEC consecutive HR pixels of one row.  The accumulator slice (2 x 3 float4) is prefetched into L2 at
+// entry and only loaded after the gathers/weights are done, so its registers are not live during the math (more
+// resident warps) while its HBM latency still overlaps the math.
+// Per-pixel front end shared by both kernels: position, tile flow, robustness, then the taps.
+// RowCtx caches the y-axis split for the flow tile of the previous pixel (4 consecutive pixels nearly always share it).
+struct RowCtx {
+    double lr_y;
+    int py, i_r;
+    int tile_x;     // flow tile column the cached split belongs to (-1: none)
+    float2 fl;
+    int ci;
+    float ty;
+    bool ok_y;
+};
+
+template <bool ISO, bool ACCUM>
+__device__ __forceinline__ void merge_hr_pixel(const MergeFrame &f, const MergeGeom &g, int hr_j, RowCtx &rc, CovQuads &cq,
+                                               float (&val)[3], float (&acc)[3]) {
+    const double lr_x = lr_coord(hr_j, g.scale, g.inv_scale, g.pow2);
+    const int ilx = (int)lr_x;
+    const int tcol = tile_of(ilx, g);
+    if (tcol != rc.tile_x) {
+        rc.tile_x = tcol;
+        rc.fl = __ldg(reinterpret_cast<const float2 *>(f.flow) + (unsigned)rc.py * (unsigned)g.nx + (unsigned)tcol);
+        rc.ok_y = split_pos(rc.lr_y, rc.fl.y, g.H, rc.ci, rc.ty);
+    }
+    int cj;
+    float tx;
+    if (!rc.ok_y || !split_pos(lr_x, rc.fl.x, g.W, cj, tx)) return;
+    const float local_r = __ldg(f.r + (unsigned)rc.i_r * (unsigned)g.W + (unsigned)min(ilx, g.W - 1));
+    merge_pixel<ISO, ACCUM>(f, g, cj, tx, rc.ci, rc.ty, local_r, cq, val, acc);
+}
+
+// Single comp frame (the reference's launch granularity, merge.py:284-287).  One thread = VEC consecutive HR pixels
+// of one row.  The accumulator slice (2 x 3 float4) is prefetched into L2 at entry and only loaded after the
+// gathers/weights are done: its registers are not live during the math (more resident warps) while its HBM latency
+// still overlaps the math.  `num += val` with val the per-frame sum, exactly as the reference.
 template <bool ISO, int VEC>
-__global__ void __launch_bounds__(256, 3) accumulate_kernel(MergeBatch b, MergeGeom g, float *__restrict__ num,
-                                                            float *__restrict__ den) {
+__global__ void __launch_bounds__(256, HHSR_MERGE_MINBLOCKS) accumulate_kernel(MergeFrame f, MergeGeom g, float *__restrict__ num,
+                                                                                float *__restrict__ den) {
+    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (hr_i >= g.Hs || j0 >= g.Ws) return;
+    const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
+    const bool full = (VEC == 4) && (j0 + VEC <= g.Ws);
+    if (VEC == 4 && (threadIdx.x & 1) == 0) {   // 2 threads share 96 B = at most 2 lines per accumulator
+        prefetch_l2(num + base);
+        prefetch_l2(den + base);
+        prefetch_l2(num + base + 23);
+        prefetch_l2(den + base + 23);
+    }
+    float n[VEC][3], d[VEC][3];
+    RowCtx rc;
+    rc.lr_y = lr_coord(hr_i, g.scale, g.inv_scale, g.pow2);                     // merge.py:319-320
+    const int ily = (int)rc.lr_y;
+    rc.py = tile_of(ily, g), rc.i_r = min(ily, g.H - 1);                         // merge.py:322-323, 335-336
+    rc.tile_x = -1;
+    CovQuads cq;
+    cq.fx0 = cq.fy0 = -1;
+#pragma unroll
+    for (int p = 0; p < VEC; ++p) {
+        n[p][0] = n[p][1] = n[p][2] = d[p][0] = d[p][1] = d[p][2] = 0.f;
+        if (j0 + p < g.Ws) merge_hr_pixel<ISO, false>(f, g, j0 + p, rc, cq, n[p], d[p]);
+    }
+    if (full) {
+        const float *nf = &n[0][0], *df = &d[0][0];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float4 a = *reinterpret_cast<const float4 *>(num + base + 4 * q);
+            float4 c = *reinterpret_cast<const float4 *>(den + base + 4 * q);
+            a.x += nf[4 * q], a.y += nf[4 * q + 1], a.z += nf[4 * q + 2], a.w += nf[4 * q + 3];
+            c.x += df[4 * q], c.y += df[4 * q + 1], c.z += df[4 * q + 2], c.w += df[4 * q + 3];
+            *reinterpret_cast<float4 *>(num + base + 4 * q) = a;
+            *reinterpret_cast<float4 *>(den + base + 4 * q) = c;
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < VEC; ++p)
+            if (j0 + p < g.Ws)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    num[base + p * 3 + c] += n[p][c];
+                    den[base + p * 3 + c] += d[p][c];
+                }
+    }
+}
+
+// K comp frames in one pass over the accumulators (B200 addition).  The slice is loaded first and the frames are
+// added in list order, so the result is bit-identical to K single-frame launches.
+template <bool ISO, int VEC>
+__global__ void __launch_bounds__(256, 2) accumulate_batch_kernel(MergeBatch b, MergeGeom g, float *__restrict__ num,
+                                                                  float *__restrict__ den) {
     const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (hr_i >= g.Hs || j0 >= g.Ws) return;
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
     const bool full = (VEC == 4) && (j0 + VEC <= g.Ws);
     float n[VEC * 3], d[VEC * 3];
-    if (full) {   // 3 x float4 per accumulator, issued before the gathers so HBM latency overlaps the math
+    if (full) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             const float4 a = *reinterpret_cast<const float4 *>(num + base + 4 * q);
@@ -166,25 +340,19 @@ __global__ void __launch_bounds__(256, 3) accumulate_kernel(MergeBatch b, MergeG
             d[q] = ok ? den[base + q] : 0.f;
         }
     }
-    const double lr_y = lr_coord(hr_i, g.scale, g.inv_scale, g.pow2);           // merge.py:319-320
-    const int ily = (int)lr_y;
-    const int py = ily / g.ts, i_r = min(ily, g.H - 1);                          // merge.py:322-323, 335-336
+    RowCtx rc;
+    rc.lr_y = lr_coord(hr_i, g.scale, g.inv_scale, g.pow2);
+    const int ily = (int)rc.lr_y;
+    rc.py = tile_of(ily, g), rc.i_r = min(ily, g.H - 1);
     for (int k = 0; k < b.K; ++k) {
-        const MergeFrame &f = b.f[k];
-        const float2 *flow_row = reinterpret_cast<const float2 *>(f.flow) + (size_t)py * g.nx;
-        const float *r_row = f.r + (size_t)i_r * g.W;
+        CovQuads cq;
+        cq.fx0 = cq.fy0 = -1;
+        rc.tile_x = -1;
 #pragma unroll
         for (int p = 0; p < VEC; ++p) {
             if (j0 + p >= g.Ws) break;
-            const double lr_x = lr_coord(j0 + p, g.scale, g.inv_scale, g.pow2);
-            const int ilx = (int)lr_x;
-            const float2 fl = __ldg(flow_row + ilx / g.ts);
-            int cj, ci;
-            float tx, ty;
-            if (!split_pos(lr_x, fl.x, g.W, cj, tx) || !split_pos(lr_y, fl.y, g.H, ci, ty)) continue;
-            const float local_r = __ldg(r_row + min(ilx, g.W - 1));
             float val[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
-            merge_pixel<ISO>(f, g, cj, tx, ci, ty, local_r, val, acc);
+            merge_hr_pixel<ISO, false>(b.f[k], g, j0 + p, rc, cq, val, acc);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 n[p * 3 + c] += val[c];
@@ -266,7 +434,7 @@ __global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__rest
         for (int j = -rad; j <= rad; ++j) {
             const int xx = cx + j;
             if (xx < 0 || xx >= g.W) continue;
-            const int chn = cfa_channel(g.cfa, yy, xx);
+            const int chn = cfa_channel(g.cfa.packed, yy, xx);
             const double c = (double)__ldg(raw + (size_t)yy * g.W + xx);
             const double dx = (double)xx - (double)pos_x, dy = (double)yy - (double)pos_y;
             double y;
@@ -324,23 +492,29 @@ static int check_merge_args(const void *raw, const void *num, const void *den, i
     return 0;
 }
 
+template <int VEC>
+static void launch_accumulate_vec(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso, dim3 grid,
+                                  dim3 block, cudaStream_t st) {
+    if (b.K == 1) {
+        if (iso)
+            accumulate_kernel<true, VEC><<<grid, block, 0, st>>>(b.f[0], g, num, den);
+        else
+            accumulate_kernel<false, VEC><<<grid, block, 0, st>>>(b.f[0], g, num, den);
+    } else {
+        if (iso)
+            accumulate_batch_kernel<true, VEC><<<grid, block, 0, st>>>(b, g, num, den);
+        else
+            accumulate_batch_kernel<false, VEC><<<grid, block, 0, st>>>(b, g, num, den);
+    }
+}
+
 static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso,
                              cudaStream_t st) {
-    const bool vec = (g.Ws % 4 == 0);
     dim3 block(32, 8);
-    if (vec) {
-        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8));
-        if (iso)
-            accumulate_kernel<true, 4><<<grid, block, 0, st>>>(b, g, num, den);
-        else
-            accumulate_kernel<false, 4><<<grid, block, 0, st>>>(b, g, num, den);
-    } else {
-        dim3 grid(ceil_div(g.Ws, 32), ceil_div(g.Hs, 8));
-        if (iso)
-            accumulate_kernel<true, 1><<<grid, block, 0, st>>>(b, g, num, den);
-        else
-            accumulate_kernel<false, 1><<<grid, block, 0, st>>>(b, g, num, den);
-    }
+    if (g.Ws % 4 == 0)
+        launch_accumulate_vec<4>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8)), block, st);
+    else
+        launch_accumulate_vec<1>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32), ceil_div(g.Hs, 8)), block, st);
     return launch_status("merge_accumulate");
 }
 

@@ -49,34 +49,55 @@ struct Taps {
 };
 constexpr int DBX = 32, DBY = 8;
 
-// dynamic smem: in[(DBY*f + 2R)][(DBX*f + 2R)] then tmp[DBY][(DBX*f + 2R)]
-__global__ void __launch_bounds__(DBX *DBY) gauss_downsample_kernel(const float *__restrict__ src, int h, int w, int f, int R,
+// smem: in[(DBY*F + 2R)][(DBX*F + 2R)] then tmp[DBY][(DBX*F + 2R)].  F = 0 selects the run-time (f, R) version;
+// the compile-time versions (F = 2, R = 4 and F = 4, R = 8: the factors of the default pyramid) unroll the taps and
+// keep all index arithmetic in shifts.
+template <int F, int RR>
+__global__ void __launch_bounds__(DBX *DBY) gauss_downsample_kernel(const float *__restrict__ src, int h, int w, int f_rt, int R_rt,
                                                                     Taps taps, float *__restrict__ dst, int h2, int w2) {
     extern __shared__ float sm[];
+    const int f = F ? F : f_rt, R = F ? RR : R_rt;
     const int K = 2 * R + 1;
     const int tin_w = DBX * f + 2 * R, tin_h = DBY * f + 2 * R;
     float *tin = sm, *tmp = sm + tin_w * tin_h;
     const int ox0 = blockIdx.x * DBX, oy0 = blockIdx.y * DBY;
     const int ix0 = ox0 * f, iy0 = oy0 * f;
     const int tid = threadIdx.y * DBX + threadIdx.x;
-    for (int t = tid; t < tin_w * tin_h; t += DBX * DBY) {
-        const int ly = t / tin_w, lx = t % tin_w;
-        const int gy = iy0 + ly, gx = ix0 + lx;
-        tin[t] = (gy < h && gx < w) ? __ldg(src + (size_t)gy * w + gx) : 0.f;
+    for (int ly = threadIdx.y; ly < tin_h; ly += DBY) {           // one warp per input row: coalesced, no div/mod
+        const int gy = iy0 + ly;
+        for (int lx = threadIdx.x; lx < tin_w; lx += DBX) {
+            const int gx = ix0 + lx;
+            tin[ly * tin_w + lx] = (gy < h && gx < w) ? __ldg(src + (size_t)gy * w + gx) : 0.f;
+        }
     }
     __syncthreads();
-    // y pass (first F.conv2d, utils_image.py:383): only the DBY kept rows
-    for (int t = tid; t < DBY * tin_w; t += DBX * DBY) {
-        const int r = t / tin_w, c = t % tin_w;
-        float acc = 0.f;
-        for (int a = 0; a < K; ++a) acc = fmaf(taps.g[a], tin[(r * f + a) * tin_w + c], acc);
-        tmp[t] = acc;
+    // y pass (first F.conv2d, utils_image.py:383): only the DBY kept rows; thread (r = threadIdx.y) sweeps columns
+    {
+        const int r = threadIdx.y;
+        for (int c = threadIdx.x; c < tin_w; c += DBX) {
+            float acc = 0.f;
+            const float *col = tin + (r * f) * tin_w + c;
+            if (F) {
+#pragma unroll
+                for (int a = 0; a < 2 * RR + 1; ++a) acc = fmaf(taps.g[a], col[a * tin_w], acc);
+            } else {
+                for (int a = 0; a < K; ++a) acc = fmaf(taps.g[a], col[a * tin_w], acc);
+            }
+            tmp[r * tin_w + c] = acc;
+        }
     }
     __syncthreads();
+    (void)tid;
     const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
     if (ox >= w2 || oy >= h2) return;
     float acc = 0.f;   // x pass (second F.conv2d, :384)
-    for (int b = 0; b < K; ++b) acc = fmaf(taps.g[b], tmp[threadIdx.y * tin_w + threadIdx.x * f + b], acc);
+    const float *rowp = tmp + threadIdx.y * tin_w + threadIdx.x * f;
+    if (F) {
+#pragma unroll
+        for (int b = 0; b < 2 * RR + 1; ++b) acc = fmaf(taps.g[b], rowp[b], acc);
+    } else {
+        for (int b = 0; b < K; ++b) acc = fmaf(taps.g[b], rowp[b], acc);
+    }
     dst[(size_t)oy * w2 + ox] = acc;
 }
 
@@ -118,11 +139,17 @@ extern "C" int hhsr_gauss_downsample(const float *src, int h, int w, int factor,
     for (int i = 0; i < 2 * radius + 1; ++i) t.g[i] = taps_host[i];
     const int tin_w = DBX * factor + 2 * radius, tin_h = DBY * factor + 2 * radius;
     const size_t smem = (size_t)(tin_w * tin_h + DBY * tin_w) * sizeof(float);
-    if (smem > 48 * 1024) {
-        if (smem > 200 * 1024) return unsupported("downsampling factor too large for one CTA tile");
-        cudaFuncSetAttribute(gauss_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
+    if (smem > 200 * 1024) return unsupported("downsampling factor too large for one CTA tile");
     dim3 block(DBX, DBY), grid(ceil_div(w2, DBX), ceil_div(h2, DBY));
-    gauss_downsample_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(src, h, w, factor, radius, t, dst, h2, w2);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (factor == 2 && radius == 4) {
+        gauss_downsample_kernel<2, 4><<<grid, block, smem, st>>>(src, h, w, factor, radius, t, dst, h2, w2);
+    } else if (factor == 4 && radius == 8) {
+        gauss_downsample_kernel<4, 8><<<grid, block, smem, st>>>(src, h, w, factor, radius, t, dst, h2, w2);
+    } else {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(gauss_downsample_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gauss_downsample_kernel<0, 0><<<grid, block, smem, st>>>(src, h, w, factor, radius, t, dst, h2, w2);
+    }
     return launch_status("gauss_downsample");
 }

@@ -218,25 +218,41 @@ __global__ void __launch_bounds__(RBX *RBY) robustness_kernel(const float *__res
         S = tile_S(fl, py, px, ny, nx, p);
     }
     const int h = H / 2, w = W / 2;
-    const size_t plane = (size_t)H * W, lplane = (size_t)h * w, o = (size_t)y * W + x;
+    const unsigned plane = (unsigned)H * (unsigned)W, lplane = (unsigned)h * (unsigned)w, o = (unsigned)y * (unsigned)W + x;
     const Axis ay = dodgson_axis(y, f.y, h), ax = dodgson_axis(x, f.x, w);
     float out = 0.f;   // any non-finite statistic ends as clamp(NaN) = 0 in the reference
     const float rm0 = __ldg(ref_means + o);
     if (ay.ok && ax.ok && isfinite(rm0)) {
         float buf[3] = {0.f, 0.f, 0.f}, wacc = 0.f;
+        if (ay.i[2] == ay.i[0] + 2 && ax.i[2] == ax.i[0] + 2) {
+            // interior: the 3x3 taps are contiguous -> one base pointer per (plane,row), immediate column offsets
+            const float *q0 = comp_lr + ((unsigned)ay.i[0] * (unsigned)w + (unsigned)ax.i[0]);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float *row = comp_lr + (size_t)ay.i[i] * w;
+            for (int c = 0; c < 3; ++c) {
+                const float *qc = q0 + c * lplane;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float wgt = ay.w[i] * ax.w[j];
-                const float *q = row + ax.i[j];
+                for (int i = 0; i < 3; ++i) {
+                    const float *row = qc + i * w;
+                    const float r3 = fmaf(__ldg(row), ax.w[0], fmaf(__ldg(row + 1), ax.w[1], __ldg(row + 2) * ax.w[2]));
+                    buf[c] = fmaf(r3, ay.w[i], buf[c]);
+                }
+            }
+            wacc = (ay.w[0] + ay.w[1] + ay.w[2]) * (ax.w[0] + ax.w[1] + ax.w[2]);
+        } else {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) buf[c] = fmaf(__ldg(q + c * lplane), wgt, buf[c]);
-                wacc += wgt;
+            for (int i = 0; i < 3; ++i) {
+                const float *row = comp_lr + (unsigned)ay.i[i] * (unsigned)w;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float wgt = ay.w[i] * ax.w[j];
+                    const float *q = row + ax.i[j];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) buf[c] = fmaf(__ldg(q + c * lplane), wgt, buf[c]);
+                    wacc += wgt;
+                }
             }
         }
-        const float inv_w = 1.0f / wacc;
+        const float inv_w = __fdividef(1.0f, wacc);
         float sigma_sq = 0.f, d_sq = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -248,10 +264,10 @@ __global__ void __launch_bounds__(RBX *RBY) robustness_kernel(const float *__res
             sigma_sq += fmaxf(sigma_p_sq, sigma_t * sigma_t);                   // :524
             const float d_p = fabsf(brightness - buf[c] * inv_w);               // :462
             const float d_p_sq = d_p * d_p;
-            const float shrink = d_p_sq / (d_p_sq + d_t * d_t);
+            const float shrink = __fdividef(d_p_sq, d_p_sq + d_t * d_t);
             d_sq += d_p_sq * shrink * shrink;
         }
-        const float e = expf(-d_sq / sigma_sq);                                  // math.exp(float32), :638
+        const float e = expf(-__fdividef(d_sq, sigma_sq));                      // math.exp(float32), :638
         double v = (double)(S * e) - p.t;
         v = (v > 0.0) ? v : 0.0;
         v = (v < 1.0) ? v : 1.0;

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhhsr.so")
+LIB_PATH = os.environ.get("HHSR_LIB", os.path.join(_HERE, "libhhsr.so"))   # HHSR_LIB: kernel-variant experiments
 
 _P, _I, _D, _F, _Z = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_size_t
 _IP, _DP, _FP = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_float)
