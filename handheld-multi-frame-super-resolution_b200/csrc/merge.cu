@@ -377,79 +377,80 @@ __global__ void __launch_bounds__(256, 2) accumulate_batch_kernel(MergeBatch b, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Reference frame (merge.py:82-233).  Once per burst: keeps the reference's float64 arithmetic.
+// Reference frame (merge.py:82-233).  The reference rounds the HR->LR position to float32 (`coarse_ref_sub_pos`
+// is a float32 local array), so tap offsets `tap - pos` and the covariance-map coordinate (pos - 0.5)/2 are exact
+// in float32; the remaining arithmetic (bilinear Omega, inverse, quadratic form, exp) is float32 here where the
+// reference promotes to float64 — float32-rounding-level differences, pinned by the goldens.
+// rows [row_begin, row_end) of the output are processed (frame-sharded runs normalise row slices).
 // ---------------------------------------------------------------------------------------------------------
 template <bool ISO>
 __global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__restrict__ raw, const float *__restrict__ covs,
                                                              MergeGeom g, float *__restrict__ num, float *__restrict__ den,
                                                              const double *__restrict__ acc_rob, int max_frame_count,
-                                                             int rad_max, double max_multiplier, int fuse_divide) {
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (ox >= g.Ws || oy >= g.Hs) return;
+                                                             int rad_max, float max_multiplier, int fuse_divide, int row_begin,
+                                                             int row_end) {
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox >= g.Ws || oy >= row_end) return;
     const float pos_y = (float)((double)oy / g.scale), pos_x = (float)((double)ox / g.scale);   // :113-114
-    float i00 = 1.f, i01 = 0.f, i10 = 0.f, i11 = 1.f;
-    if (!ISO) {
-        const float gy = (float)(((double)pos_y - 0.5) / 2.0), gx = (float)(((double)pos_x - 0.5) / 2.0);
+    const float kS = -0.72134752044448170368f;   // -0.5 * log2(e)
+    float qxx, qxy, qyy;
+    if (ISO) {
+        qxx = qyy = 2.0f * kS, qxy = 0.f;                                                        // :211
+    } else {
+        const float gy = (pos_y - 0.5f) * 0.5f, gx = (pos_x - 0.5f) * 0.5f;                      // :132-133 (exact)
         const int fx0 = (int)fmaxf(floorf(gx), 0.f), fy0 = (int)fmaxf(floorf(gy), 0.f);
         const int cx1 = min(fx0 + 1, g.cw - 1), cy1 = min(fy0 + 1, g.ch - 1);
-        const double rx = (double)(gx - truncf(gx)), ry = (double)(gy - truncf(gy));            // linalg.py:190-191
+        const float rx = gx - truncf(gx), ry = gy - truncf(gy);                                  // linalg.py:190-191
         const float4 *c4 = reinterpret_cast<const float4 *>(covs);
-        const float4 c00 = __ldg(c4 + (size_t)fy0 * g.cw + fx0), c01 = __ldg(c4 + (size_t)fy0 * g.cw + cx1);
-        const float4 c10 = __ldg(c4 + (size_t)cy1 * g.cw + fx0), c11 = __ldg(c4 + (size_t)cy1 * g.cw + cx1);
-        const double w00 = (1 - rx) * (1 - ry), w01 = rx * (1 - ry), w10 = (1 - rx) * ry, w11 = rx * ry;
-        // linalg.py:194-199: ((a*(1-rx))*(1-ry) + ...) evaluated left to right in float64, stored float32
-        auto mix = [&](float a, float b, float c, float d) {
-            return (float)((double)a * (1 - rx) * (1 - ry) + (double)b * rx * (1 - ry) + (double)c * (1 - rx) * ry +
-                           (double)d * rx * ry);
-        };
-        (void)w00, (void)w01, (void)w10, (void)w11;
-        const float m00 = mix(c00.x, c01.x, c10.x, c11.x), m01 = mix(c00.y, c01.y, c10.y, c11.y);
-        const float m10 = mix(c00.z, c01.z, c10.z, c11.z), m11 = mix(c00.w, c01.w, c10.w, c11.w);
-        const float det = m00 * m11 - m01 * m10;                                                 // linalg.py:53
-        if (fabs((double)det) > 1e-10) {
-            const double det_i = 1.0 / (double)det;
-            i00 = (float)((double)m11 * det_i);
-            i01 = (float)((double)(-m01) * det_i);
-            i10 = (float)((double)(-m10) * det_i);
-            i11 = (float)((double)m00 * det_i);
+        const float4 c00 = __ldg(c4 + (unsigned)fy0 * (unsigned)g.cw + fx0), c01 = __ldg(c4 + (unsigned)fy0 * (unsigned)g.cw + cx1);
+        const float4 c10 = __ldg(c4 + (unsigned)cy1 * (unsigned)g.cw + fx0), c11 = __ldg(c4 + (unsigned)cy1 * (unsigned)g.cw + cx1);
+        const float w00 = (1.f - rx) * (1.f - ry), w01 = rx * (1.f - ry), w10 = (1.f - rx) * ry, w11 = rx * ry;
+        const float m00 = c00.x * w00 + c01.x * w01 + c10.x * w10 + c11.x * w11;
+        const float m01 = c00.y * w00 + c01.y * w01 + c10.y * w10 + c11.y * w11;
+        const float m10 = c00.z * w00 + c01.z * w01 + c10.z * w10 + c11.z * w11;
+        const float m11 = c00.w * w00 + c01.w * w01 + c10.w * w10 + c11.w * w11;
+        const float det = __fmaf_rn(m00, m11, -__fmul_rn(m01, m10));                             // linalg.py:53
+        float i00 = 1.f, i0110 = 0.f, i11 = 1.f;
+        if (fabsf(det) > 1e-10f) {                                                               // EPSILON_DIV
+            const float det_i = 1.0f / det;
+            i00 = m11 * det_i, i0110 = -(m01 + m10) * det_i, i11 = m00 * det_i;
         }
+        qxx = kS * i00, qxy = kS * i0110, qyy = kS * i11;                                        // linalg.py:83
     }
-    double power = 1.0;
     int rad = 1;
     bool overwrite = false;
     if (acc_rob != nullptr) {                                                                    // :167-176
-        const int ay = min((int)llrint((double)pos_y), g.H - 1), ax = min((int)llrint((double)pos_x), g.W - 1);
-        const double la = acc_rob[(size_t)ay * g.W + ax];
+        const int ay = min((int)rintf(pos_y), g.H - 1), ax = min((int)rintf(pos_x), g.W - 1);
+        const double la = __ldg(acc_rob + (size_t)ay * g.W + ax);
         if (la <= (double)max_frame_count) {
-            power = max_multiplier;
+            const float inv_p = 1.0f / max_multiplier;                                           // y /= power, :218
+            qxx *= inv_p, qxy *= inv_p, qyy *= inv_p;
             rad = rad_max;
         }
         overwrite = la < (double)max_frame_count;
     }
-    const int cx = (int)llrint((double)pos_x), cy = (int)llrint((double)pos_y);                  // round half even
+    const int cx = (int)rintf(pos_x), cy = (int)rintf(pos_y);                                    // round half even
     float val[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
     for (int i = -rad; i <= rad; ++i) {
         const int yy = cy + i;
         if (yy < 0 || yy >= g.H) continue;
+        const float dy = (float)yy - pos_y;
+        const float qy = qyy * dy * dy, qm = qxy * dy;
         for (int j = -rad; j <= rad; ++j) {
             const int xx = cx + j;
             if (xx < 0 || xx >= g.W) continue;
             const int chn = cfa_channel(g.cfa.packed, yy, xx);
-            const double c = (double)__ldg(raw + (size_t)yy * g.W + xx);
-            const double dx = (double)xx - (double)pos_x, dy = (double)yy - (double)pos_y;
-            double y;
-            if (ISO)
-                y = 2 * (dx * dx + dy * dy);
-            else
-                y = (double)i00 * dx * dx + dx * dy * (double)(i01 + i10) + (double)i11 * dy * dy;  // linalg.py:83
-            y = (y > 0) ? y : 0.0;
-            y /= power;
-            const double w = exp(-0.5 * y);
+            const float c = __ldg(raw + (unsigned)yy * (unsigned)g.W + xx);
+            const float dx = (float)xx - pos_x;
+            const float z = fminf(0.f, (qxx * dx + qm) * dx + qy);                               // max(0, y): NaN -> 0
+            // The reference's float32 accumulators keep weights down to the subnormal range (1e-45) and a channel
+            // fed only by far taps of a narrow kernel is normalised from exactly those: evaluate them in float64.
+            const float w = (z > -120.f) ? ex2_approx(z) : (float)exp2((double)z);
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 if (chn == k) {
-                    val[k] = (float)((double)val[k] + c * w);
-                    acc[k] = (float)((double)acc[k] + w);
+                    val[k] = fmaf(c, w, val[k]);
+                    acc[k] += w;
                 }
         }
     }
@@ -553,19 +554,22 @@ extern "C" int hhsr_merge_accumulate(const float *raw, int H, int W, const float
 
 extern "C" int hhsr_merge_ref(const float *raw, int H, int W, const float *covs, float *num, float *den, int Hs,
                               int Ws, double scale, const int *cfa_host, int iso, const double *acc_rob,
-                              int max_frame_count, int rad_max, double max_multiplier, int fuse_divide,
-                              hhsr_stream_t stream) {
+                              int max_frame_count, int rad_max, double max_multiplier, int fuse_divide, int row_begin,
+                              int row_end, hhsr_stream_t stream) {
     if (int e = check_merge_args(raw, num, den, H, W, Hs, Ws, scale, cfa_host)) return e;
     HHSR_REQUIRE(iso || (covs && (uintptr_t)covs % 16 == 0), "covs required (16-byte aligned) for the steerable kernel");
-    HHSR_REQUIRE(acc_rob == nullptr || rad_max >= 0, "rad_max must be >= 0");
+    HHSR_REQUIRE(acc_rob == nullptr || (rad_max >= 0 && max_multiplier > 0.0), "rad_max >= 0 and max_multiplier > 0 required");
+    HHSR_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= Hs, "row range must satisfy 0 <= begin < end <= Hs");
     MergeGeom g = make_geom(H, W, 0, 1, Hs, Ws, cfa_host, scale);
-    dim3 block(32, 8), grid(ceil_div(Ws, 32), ceil_div(Hs, 8));
+    dim3 block(32, 8), grid(ceil_div(Ws, 32), ceil_div(row_end - row_begin, 8));
     if (iso)
         accumulate_ref_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(raw, covs, g, num, den, acc_rob, max_frame_count,
-                                                                             rad_max, max_multiplier, fuse_divide);
+                                                                             rad_max, (float)max_multiplier, fuse_divide,
+                                                                             row_begin, row_end);
     else
         accumulate_ref_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(raw, covs, g, num, den, acc_rob, max_frame_count,
-                                                                              rad_max, max_multiplier, fuse_divide);
+                                                                              rad_max, (float)max_multiplier, fuse_divide,
+                                                                              row_begin, row_end);
     return launch_status("merge_ref");
 }
 

@@ -158,8 +158,33 @@ __global__ void __launch_bounds__(RBX *RBY) upscale_warp_kernel(const float *__r
         const float2 f = __ldg(reinterpret_cast<const float2 *>(flow) + (size_t)(y / ts) * nx + x / ts);
         fx = f.x, fy = f.y;
     }
+    // float32 taps from the exact integer/fraction position split (see dodgson_axis); the float64 sampler above is
+    // kept as the literal restatement and used when HHSR_DODGSON_F64 is defined
+#ifdef HHSR_DODGSON_F64
     float v[3];
     const bool ok = dodgson_sample(lr, h, w, y, x, fx, fy, v);
+#else
+    const Axis ay = dodgson_axis(y, fy, h), ax = dodgson_axis(x, fx, w);
+    const bool ok = ay.ok && ax.ok;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (ok) {
+        const unsigned lplane = (unsigned)h * (unsigned)w;
+        float wacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float *row = lr + (unsigned)ay.i[i] * (unsigned)w;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float wgt = ay.w[i] * ax.w[j];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = fmaf(__ldg(row + ax.i[j] + c * lplane), wgt, v[c]);
+                wacc += wgt;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = v[c] / wacc;
+    }
+#endif
     const size_t plane = (size_t)H * W, o = (size_t)y * W + x;
 #pragma unroll
     for (int c = 0; c < 3; ++c) hr[o + c * plane] = ok ? v[c] : INFINITY;

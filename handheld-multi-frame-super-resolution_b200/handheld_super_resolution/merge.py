@@ -42,10 +42,11 @@ def merge_batch(comp_imgs, alignments, covs, rs, num, den, cfa_pattern, config):
               num.shape[1], float(config.scale), _lib.cfa_array(cfa_pattern), int(iso), _lib.stream())
 
 
-def merge_ref(ref_img, kernels, num, den, cfa_pattern, config, acc_rob=None, fuse_divide=False):
+def merge_ref(ref_img, kernels, num, den, cfa_pattern, config, acc_rob=None, fuse_divide=False, rows=None):
     """Accumulate the reference frame (merge.py:22-80).  With the accumulated-robustness denoiser enabled,
     `acc_rob` (float64 [H,W]) widens the window / overwrites the accumulators where few frames were merged.
-    fuse_divide=True also performs utils.divide(num, den) in the same pass (B200 addition)."""
+    fuse_divide=True also performs utils.divide(num, den) in the same pass; rows=(begin, end) restricts the work
+    to a slice of output rows (both B200 additions, used by the frame-sharded driver)."""
     if config.mode != "bayer":
         raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
     _check_acc(num, den)
@@ -62,4 +63,4 @@ def merge_ref(ref_img, kernels, num, den, cfa_pattern, config, acc_rob=None, fus
         acc, rad_max, max_mult, max_fc = None, 0, 0.0, 0
     _lib.call("hhsr_merge_ref", _lib.ptr(ref_img), H, W, _lib.ptr(None if iso else kernels), _lib.ptr(num), _lib.ptr(den),
               num.shape[0], num.shape[1], float(config.scale), _lib.cfa_array(cfa_pattern), int(iso), _lib.ptr(acc),
-              max_fc, rad_max, max_mult, int(fuse_divide), _lib.stream())
+              max_fc, rad_max, max_mult, int(fuse_divide), *(rows if rows is not None else (0, num.shape[0])), _lib.stream())

@@ -103,12 +103,19 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
         if debug_mode:
             debug_dict["robustness"].append(r.cpu().numpy())
 
+    # the one reduction point of the pipeline (frame-sharded runs): reduce_fn sums the accumulators across ranks and
+    # may hand back the slice of output rows this rank has to normalise plus a callable that re-assembles the image
+    rows, gather_fn = None, None
     if reduce_fn is not None:
-        reduce_fn(num, den, accumulated_r)
+        res = reduce_fn(num, den, accumulated_r)
+        if res is not None:
+            rows, gather_fn = res
 
     covs = estimate_kernels_(cuda_ref_img, config)
     use_acc = accumulated_r if config.accumulated_robustness_denoiser.enabled else None
-    merge_ref_(cuda_ref_img, covs, num, den, cfa_pattern, config, use_acc, fuse_divide=True)   # + utils.divide, :191
+    merge_ref_(cuda_ref_img, covs, num, den, cfa_pattern, config, use_acc, fuse_divide=True, rows=rows)   # + utils.divide, :191
+    if gather_fn is not None:
+        gather_fn(num)
 
     if config.verbose >= 1:
         torch.cuda.synchronize()

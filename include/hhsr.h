@@ -120,10 +120,12 @@ int hhsr_merge_accumulate_batch(const float *const *raws, const float *const *fl
                                 hhsr_stream_t stream);
 /* ---- merge of the reference frame, Alg. 11 (merge.py:22-233).  acc_rob (float64 [H][W]) may be NULL; when given,
  * the accumulated-robustness denoiser rules apply (widened window / overwrite).  fuse_divide != 0 additionally
- * performs utils.divide (num <- num/den) in the same pass. */
+ * performs utils.divide (num <- num/den) in the same pass.  Only output rows [row_begin, row_end) are processed
+ * (0, Hs for the whole image; frame-sharded runs normalise one row slice per GPU). */
 int hhsr_merge_ref(const float *raw, int H, int W, const float *covs, float *num, float *den, int Hs, int Ws,
                    double scale, const int *cfa_host, int iso, const double *acc_rob, int max_frame_count,
-                   int rad_max, double max_multiplier, int fuse_divide, hhsr_stream_t stream);
+                   int rad_max, double max_multiplier, int fuse_divide, int row_begin, int row_end,
+                   hhsr_stream_t stream);
 
 /* ---- element-wise helpers (utils.py:62-120) */
 int hhsr_divide(float *num, const float *den, size_t n, hhsr_stream_t stream);
