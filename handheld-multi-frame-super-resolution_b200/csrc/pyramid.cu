@@ -12,8 +12,10 @@ namespace hhsr {
 
 // keep flag of the reference's mask on the UNSHIFTED frequency index k of an axis of length n:
 // shifted index s = (k + n/2) mod n is kept iff n/4 <= s < n - ceil(n/4)   (utils_image.py:92-95)
-__device__ __forceinline__ bool band_keep(int k, int n) {
-    const int s = (k + n / 2) % n;
+__device__ __forceinline__ bool band_keep(int k, int n) {   // 0 <= k <= n
+    int s = k + n / 2;
+    s -= (s >= n) ? n : 0;
+    s -= (s >= n) ? n : 0;   // k == n (the partner of k == 0)
     return s >= n / 4 && s < n - (n + 3) / 4;
 }
 
@@ -25,7 +27,7 @@ __global__ void grey_band_mask_kernel(float2 *__restrict__ spec, int H, int W, i
     const int kx = xfast ? f : s, ky = xfast ? s : f;
     if (kx >= Wc || ky >= H) return;
     const float a = (band_keep(ky, H) && band_keep(kx, W)) ? 0.5f : 0.f;
-    const float b = (band_keep((H - ky) % H, H) && band_keep((W - kx) % W, W)) ? 0.5f : 0.f;
+    const float b = (band_keep(H - ky, H) && band_keep(W - kx, W)) ? 0.5f : 0.f;   // k = n wraps to 0 inside
     const float m = a + b;   // Re(ifft2(M F)) == ifft2(0.5 (M(k) + M(-k)) F) for a real image
     float2 *p = spec + (long long)ky * sy + (long long)kx * sx;
     if (m == 0.f)

@@ -212,43 +212,76 @@ __device__ __forceinline__ float tile_S(const float2 *__restrict__ fl, int py, i
     return ((double)(d0 * d0 + d1 * d1) > p.Mt * p.Mt) ? (float)p.s1 : (float)p.s2;
 }
 
+// (sigma_t^2, d_t^2) per brightness level as float32 pairs, so the per-pixel lookup is one 8-byte load
+__global__ void noise_table_kernel(const double *__restrict__ std_curve, const double *__restrict__ diff_curve, int n,
+                                   float2 *__restrict__ table) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) table[i] = make_float2((float)(std_curve[i] * std_curve[i]), (float)(diff_curve[i] * diff_curve[i]));
+}
+
+// Noise model + threshold for one pixel given its warped comp means (robustness.py:452-462, 504-533, 626-639)
+__device__ __forceinline__ float robustness_value(const float (&cm)[3], float rm0, const float *__restrict__ ref_means,
+                                                  const float *__restrict__ ref_vars, unsigned o, unsigned plane,
+                                                  const float2 *__restrict__ table, const RobParams &p, float S) {
+    float sigma_sq = 0.f, d_sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float brightness = c == 0 ? rm0 : __ldg(ref_means + o + c * plane);
+        int id = (int)llrint(1000.0 * (double)brightness);                  // robustness.py:519 (float64 product)
+        id = min(max(id, 0), p.n_curve - 1);
+        const float2 t = __ldg(table + id);
+        const float sigma_p_sq = __ldg(ref_vars + o + c * plane);
+        sigma_sq += fmaxf(sigma_p_sq, t.x);                                 // max(sigma_p^2, sigma_t^2), :524
+        const float d_p = fabsf(brightness - cm[c]);                        // :462
+        const float d_p_sq = d_p * d_p;
+        const float shrink = __fdividef(d_p_sq, d_p_sq + t.y);
+        d_sq += d_p_sq * shrink * shrink;
+    }
+    const float e = expf(-__fdividef(d_sq, sigma_sq));                      // math.exp(float32), :638
+    const float v = (float)((double)(S * e) - p.t);
+    return fminf(1.f, fmaxf(0.f, v));                                       // NaN -> 0
+}
+
+// One thread per raw pixel.  When the tile size is a multiple of 32 a 32x8 block lies inside one flow tile: flow,
+// S and the Dodgson axes (8 row axes + 32 column axes instead of 2 per thread) are then computed once per block.
 __global__ void __launch_bounds__(RBX *RBY) robustness_kernel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
                                                               const float *__restrict__ ref_vars, int H, int W,
                                                               const float *__restrict__ flow, int ny, int nx, int ts,
-                                                              const double *__restrict__ std_curve,
-                                                              const double *__restrict__ diff_curve, RobParams p,
+                                                              const float2 *__restrict__ table, RobParams p,
                                                               float *__restrict__ R) {
     const int x = blockIdx.x * RBX + threadIdx.x, y = blockIdx.y * RBY + threadIdx.y;
     const float2 *fl = reinterpret_cast<const float2 *>(flow);
-    // a 32x8 block lies inside one flow tile when ts is a multiple of 32: flow and S are then block-uniform
+    const int h = H / 2, w = W / 2;
     __shared__ float s_S;
-    __shared__ float2 s_f;
+    __shared__ Axis s_ay[RBY], s_ax[RBX];
     const bool uniform = (ts % RBX) == 0;
-    if (uniform) {
-        if (threadIdx.x == 0 && threadIdx.y == 0) {
-            const int py = (blockIdx.y * RBY) / ts, px = (blockIdx.x * RBX) / ts;
-            s_f = __ldg(fl + (size_t)py * nx + px);
-            s_S = tile_S(fl, py, px, ny, nx, p);
-        }
-        __syncthreads();
-    }
-    if (x >= W || y >= H) return;
-    float2 f;
+    Axis ay, ax;
     float S;
     if (uniform) {
-        f = s_f, S = s_S;
+        const int tid = threadIdx.y * RBX + threadIdx.x;
+        const int py = (blockIdx.y * RBY) / ts, px = (blockIdx.x * RBX) / ts;
+        const float2 f = __ldg(fl + (size_t)py * nx + px);
+        if (tid < RBX)
+            s_ax[tid] = dodgson_axis(min(blockIdx.x * RBX + tid, W - 1), f.x, w);
+        else if (tid < RBX + RBY)
+            s_ay[tid - RBX] = dodgson_axis(min(blockIdx.y * RBY + tid - RBX, H - 1), f.y, h);
+        else if (tid == RBX + RBY)
+            s_S = tile_S(fl, py, px, ny, nx, p);
+        __syncthreads();
+        if (x >= W || y >= H) return;
+        ay = s_ay[threadIdx.y], ax = s_ax[threadIdx.x], S = s_S;
     } else {
+        if (x >= W || y >= H) return;
         const int py = y / ts, px = x / ts;
-        f = __ldg(fl + (size_t)py * nx + px);
+        const float2 f = __ldg(fl + (size_t)py * nx + px);
         S = tile_S(fl, py, px, ny, nx, p);
+        ay = dodgson_axis(y, f.y, h), ax = dodgson_axis(x, f.x, w);
     }
-    const int h = H / 2, w = W / 2;
     const unsigned plane = (unsigned)H * (unsigned)W, lplane = (unsigned)h * (unsigned)w, o = (unsigned)y * (unsigned)W + x;
-    const Axis ay = dodgson_axis(y, f.y, h), ax = dodgson_axis(x, f.x, w);
     float out = 0.f;   // any non-finite statistic ends as clamp(NaN) = 0 in the reference
     const float rm0 = __ldg(ref_means + o);
     if (ay.ok && ax.ok && isfinite(rm0)) {
-        float buf[3] = {0.f, 0.f, 0.f}, wacc = 0.f;
+        float buf[3] = {0.f, 0.f, 0.f}, wacc;
         if (ay.i[2] == ay.i[0] + 2 && ax.i[2] == ax.i[0] + 2) {
             // interior: the 3x3 taps are contiguous -> one base pointer per (plane,row), immediate column offsets
             const float *q0 = comp_lr + ((unsigned)ay.i[0] * (unsigned)w + (unsigned)ax.i[0]);
@@ -264,6 +297,7 @@ __global__ void __launch_bounds__(RBX *RBY) robustness_kernel(const float *__res
             }
             wacc = (ay.w[0] + ay.w[1] + ay.w[2]) * (ax.w[0] + ax.w[1] + ax.w[2]);
         } else {
+            wacc = 0.f;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const float *row = comp_lr + (unsigned)ay.i[i] * (unsigned)w;
@@ -278,25 +312,8 @@ __global__ void __launch_bounds__(RBX *RBY) robustness_kernel(const float *__res
             }
         }
         const float inv_w = __fdividef(1.0f, wacc);
-        float sigma_sq = 0.f, d_sq = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float brightness = c == 0 ? rm0 : __ldg(ref_means + o + c * plane);
-            long long id = llrint(1000.0 * (double)brightness);                 // robustness.py:519
-            id = id < 0 ? 0 : (id >= p.n_curve ? p.n_curve - 1 : id);
-            const float d_t = (float)__ldg(diff_curve + id), sigma_t = (float)__ldg(std_curve + id);
-            const float sigma_p_sq = __ldg(ref_vars + o + c * plane);
-            sigma_sq += fmaxf(sigma_p_sq, sigma_t * sigma_t);                   // :524
-            const float d_p = fabsf(brightness - buf[c] * inv_w);               // :462
-            const float d_p_sq = d_p * d_p;
-            const float shrink = __fdividef(d_p_sq, d_p_sq + d_t * d_t);
-            d_sq += d_p_sq * shrink * shrink;
-        }
-        const float e = expf(-__fdividef(d_sq, sigma_sq));                      // math.exp(float32), :638
-        double v = (double)(S * e) - p.t;
-        v = (v > 0.0) ? v : 0.0;
-        v = (v < 1.0) ? v : 1.0;
-        out = (float)v;
+        const float cm[3] = {buf[0] * inv_w, buf[1] * inv_w, buf[2] * inv_w};
+        out = robustness_value(cm, rm0, ref_means, ref_vars, o, plane, table, p, S);
     }
     R[o] = out;
 }
@@ -305,19 +322,22 @@ __global__ void __launch_bounds__(RBX *RBY) local_min5_kernel(const float *__res
                                                               double *__restrict__ acc_rob) {
     __shared__ float s[RBY + 4][RBX + 4];
     const int x0 = blockIdx.x * RBX, y0 = blockIdx.y * RBY;
-    for (int t = threadIdx.y * RBX + threadIdx.x; t < (RBY + 4) * (RBX + 4); t += RBX * RBY) {
-        const int ly = t / (RBX + 4), lx = t % (RBX + 4);
-        const int gy = min(max(y0 + ly - 2, 0), H - 1), gx = min(max(x0 + lx - 2, 0), W - 1);
-        s[ly][lx] = __ldg(R + (size_t)gy * W + gx);
+    for (int ly = threadIdx.y; ly < RBY + 4; ly += RBY) {
+        const int gy = min(max(y0 + ly - 2, 0), H - 1);
+        for (int lx = threadIdx.x; lx < RBX + 4; lx += RBX) {
+            const int gx = min(max(x0 + lx - 2, 0), W - 1);
+            s[ly][lx] = __ldg(R + (size_t)gy * W + gx);
+        }
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= W || y >= H) return;
     float m = INFINITY;
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int j = 0; j < 5; ++j) m = fminf(m, s[threadIdx.y + i][threadIdx.x + j]);
+    for (int i = 0; i < 5; ++i) {
+        const float *q = &s[threadIdx.y + i][threadIdx.x];
+        m = fminf(m, fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])), q[4]));
+    }
     const size_t o = (size_t)y * W + x;
     r[o] = m;
     if (acc_rob) acc_rob[o] += (double)m;
@@ -352,18 +372,28 @@ extern "C" int hhsr_upscale_warp_stats(const float *lr, int h, int w, const floa
     return launch_status("upscale_warp_stats");
 }
 
+extern "C" int hhsr_noise_table(const double *std_curve, const double *diff_curve, int n_curve, float *table,
+                                hhsr_stream_t stream) {
+    HHSR_REQUIRE(std_curve && diff_curve && table, "null pointer");
+    HHSR_REQUIRE(n_curve > 0, "empty noise curves");
+    HHSR_REQUIRE((uintptr_t)table % 8 == 0, "table must be 8-byte aligned");
+    noise_table_kernel<<<ceil_div(n_curve, 256), 256, 0, (cudaStream_t)stream>>>(std_curve, diff_curve, n_curve,
+                                                                                reinterpret_cast<float2 *>(table));
+    return launch_status("noise_table");
+}
+
 extern "C" int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_vars, int H,
-                               int W, const float *flow, int ny, int nx, int ts, const double *std_curve,
-                               const double *diff_curve, int n_curve, double t, double s1, double s2, double Mt,
-                               float *R, hhsr_stream_t stream) {
-    HHSR_REQUIRE(comp_means_lr && ref_means && ref_vars && flow && std_curve && diff_curve && R, "null pointer");
+                               int W, const float *flow, int ny, int nx, int ts, const float *noise_table, int n_curve,
+                               double t, double s1, double s2, double Mt, float *R, hhsr_stream_t stream) {
+    HHSR_REQUIRE(comp_means_lr && ref_means && ref_vars && flow && noise_table && R, "null pointer");
     HHSR_REQUIRE(H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "frame sides must be even");
     HHSR_REQUIRE(ts > 0 && ny * ts >= H && nx * ts >= W, "flow grid does not cover the frame");
     HHSR_REQUIRE(n_curve > 0, "empty noise curves");
+    HHSR_REQUIRE((uintptr_t)noise_table % 8 == 0, "noise table must be 8-byte aligned");
     RobParams p{t, s1, s2, Mt, n_curve};
     dim3 block(RBX, RBY), grid(ceil_div(W, RBX), ceil_div(H, RBY));
     robustness_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(comp_means_lr, ref_means, ref_vars, H, W, flow, ny, nx, ts,
-                                                               std_curve, diff_curve, p, R);
+                                                               reinterpret_cast<const float2 *>(noise_table), p, R);
     return launch_status("robustness");
 }
 

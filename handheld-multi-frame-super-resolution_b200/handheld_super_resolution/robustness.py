@@ -44,6 +44,20 @@ def init_robustness(ref_img, cfa_pattern, white_balance, config):
     return upscale_warp_stats(means), upscale_warp_stats(vars_)
 
 
+def noise_table(noise_model):
+    """(std_curve, diff_curve) -> float32 device table [n, 2] of (sigma_t^2, d_t^2).  Accepts an already built table
+    (main() builds it once per burst)."""
+    if isinstance(noise_model, torch.Tensor):
+        return noise_model
+    std_curve, diff_curve = noise_model
+    std_curve = _lib.as_device(std_curve, torch.float64)
+    diff_curve = _lib.as_device(diff_curve, torch.float64)
+    assert std_curve.numel() == diff_curve.numel()
+    table = torch.empty((std_curve.numel(), 2), dtype=torch.float32, device=std_curve.device)
+    _lib.call("hhsr_noise_table", _lib.ptr(std_curve), _lib.ptr(diff_curve), std_curve.numel(), _lib.ptr(table), _lib.stream())
+    return table
+
+
 def local_min(R, acc_rob=None):
     """5x5 local minimum (Alg. 9, robustness.py:641-687); optionally fused with `acc_rob += r` (utils.add)."""
     R = _lib.as_device(R)
@@ -65,14 +79,12 @@ def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pat
         raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
     tun = config.robustness.tuning
     ts = config.block_matching.tuning.tile_size
-    std_curve, diff_curve = noise_model
-    std_curve = _lib.as_device(std_curve, torch.float64)
-    diff_curve = _lib.as_device(diff_curve, torch.float64)
+    table = noise_table(noise_model)
     flows = _lib.as_device(flows)
     comp_means, _ = compute_guide_stats(comp_img, cfa_pattern, white_balance, need_vars=False)
     R = torch.empty((H, W), dtype=torch.float32, device=comp_img.device)
     _lib.call("hhsr_robustness", _lib.ptr(comp_means), _lib.ptr(ref_local_means), _lib.ptr(ref_local_stds), H, W,
-              _lib.ptr(flows), flows.shape[0], flows.shape[1], int(ts), _lib.ptr(std_curve), _lib.ptr(diff_curve),
-              std_curve.numel(), float(tun.t), float(tun.s1), float(tun.s2), float(tun.Mt), _lib.ptr(R), _lib.stream())
+              _lib.ptr(flows), flows.shape[0], flows.shape[1], int(ts), _lib.ptr(table), table.shape[0],
+              float(tun.t), float(tun.s1), float(tun.s2), float(tun.Mt), _lib.ptr(R), _lib.stream())
     r = local_min(R, acc_rob)
     return (r, R) if return_R else r

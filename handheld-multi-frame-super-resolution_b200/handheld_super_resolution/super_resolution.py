@@ -53,8 +53,9 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
     cuda_ref_img = _upload(ref_img)
     cfa_pattern = config.exif.cfa_pattern
     white_balance = config.exif.white_balance
-    std_curve = _lib.as_device(np.asarray(config.noise_model.std_curve, dtype=np.float64), torch.float64)
-    diff_curve = _lib.as_device(np.asarray(config.noise_model.diff_curve, dtype=np.float64), torch.float64)
+    from .robustness import noise_table
+    noise_tab = noise_table((np.asarray(config.noise_model.std_curve, dtype=np.float64),
+                             np.asarray(config.noise_model.diff_curve, dtype=np.float64))) if config.robustness.enabled else None
 
     cuda_ref_grey = compute_grey_images(cuda_ref_img, grey_method)
     ref_pyramid, tyled_pyr, ref_tiled_fft, ref_gradx, ref_grady, ref_hessian = init_alignment_(cuda_ref_grey, config)
@@ -95,7 +96,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
         if debug_mode:
             debug_dict["flow"].append(flow.cpu().numpy())
         r = compute_robustness_(cuda_img, ref_local_means, ref_local_stds, flow, cfa_pattern, white_balance,
-                                (std_curve, diff_curve), config, acc_rob=accumulated_r if config.robustness.enabled else None)
+                                noise_tab, config, acc_rob=accumulated_r if config.robustness.enabled else None)
         if accumulate_r and not config.robustness.enabled:
             accumulated_r += r
         covs = estimate_kernels_(cuda_img, config)

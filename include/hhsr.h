@@ -97,12 +97,15 @@ int hhsr_guide_stats(const float *raw, int H, int W, const int *cfa_host, const 
  * (robustness.py:296-418); +inf where the source position leaves the guide image. */
 int hhsr_upscale_warp_stats(const float *lr, int h, int w, const float *flow, int ny, int nx, int ts, float *hr,
                             hhsr_stream_t stream);
+/* noise curves (float64, n_curve entries, as the reference uploads them, super_resolution.py:98-99) -> float32 table
+ * [n_curve][2] = (sigma_t^2, d_t^2) read by hhsr_robustness; build once per burst. */
+int hhsr_noise_table(const double *std_curve, const double *diff_curve, int n_curve, float *table, hhsr_stream_t stream);
 /* fused per-pixel robustness (robustness.py:421-639): warped Dodgson upsampling of the comp guide means,
  * |mean difference|, noise-model shrinkage, flow-irregularity factor S and threshold -> R [H][W].
- * ref_means/ref_vars: [3][H][W] from hhsr_upscale_warp_stats; curves: float64 device arrays of n_curve entries. */
+ * ref_means/ref_vars: [3][H][W] from hhsr_upscale_warp_stats; noise_table from hhsr_noise_table. */
 int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_vars, int H, int W,
-                    const float *flow, int ny, int nx, int ts, const double *std_curve, const double *diff_curve,
-                    int n_curve, double t, double s1, double s2, double Mt, float *R, hhsr_stream_t stream);
+                    const float *flow, int ny, int nx, int ts, const float *noise_table, int n_curve, double t,
+                    double s1, double s2, double Mt, float *R, hhsr_stream_t stream);
 /* 5x5 edge-replicated local minimum (robustness.py:641-687); when acc_rob != NULL also acc_rob += r
  * (utils.py:93-120, float64 accumulator). */
 int hhsr_local_min5(const float *R, int H, int W, float *r, double *acc_rob, hhsr_stream_t stream);
