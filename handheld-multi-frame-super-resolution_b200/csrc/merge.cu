@@ -479,6 +479,20 @@ __global__ void divide_kernel(float *__restrict__ num, const float *__restrict__
     }
 }
 
+// A += B_0 + B_1 + ... in list order (float64 accumulation): K x utils.add (utils.py:93-120) in one pass over A
+struct AddList {
+    const float *b[kMaxBatch];
+    int K;
+};
+__global__ void add_many_f64_f32_kernel(double *__restrict__ A, AddList l, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a = A[i];
+        for (int k = 0; k < l.K; ++k) a += (double)__ldg(l.b[k] + i);
+        A[i] = a;
+    }
+}
+
 __global__ void add_f64_f32_kernel(double *__restrict__ A, const float *__restrict__ B, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) A[i] += (double)B[i];
@@ -581,6 +595,23 @@ extern "C" int hhsr_divide(float *num, const float *den, size_t n, hhsr_stream_t
     if (blocks > 148 * 32) blocks = 148 * 32;
     divide_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(num, den, n);
     return launch_status("divide");
+}
+
+extern "C" int hhsr_add_many_f64_f32(double *A, const float *const *Bs, int K, size_t n, hhsr_stream_t stream) {
+    HHSR_REQUIRE(A && Bs && K > 0 && n > 0, "null pointer or empty list");
+    const int block = 256;
+    size_t blocks = (n + block - 1) / block;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    for (int k0 = 0; k0 < K; k0 += kMaxBatch) {
+        AddList l;
+        l.K = (K - k0 < kMaxBatch) ? K - k0 : kMaxBatch;
+        for (int k = 0; k < l.K; ++k) {
+            HHSR_REQUIRE(Bs[k0 + k], "null array in list");
+            l.b[k] = Bs[k0 + k];
+        }
+        add_many_f64_f32_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(A, l, n);
+    }
+    return launch_status("add_many");
 }
 
 extern "C" int hhsr_add_f64_f32(double *A, const float *B, size_t n, hhsr_stream_t stream) {

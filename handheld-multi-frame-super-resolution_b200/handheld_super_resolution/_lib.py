@@ -40,6 +40,7 @@ SIGNATURES = {
     "hhsr_merge_ref": [_P, _I, _I, _P, _P, _P, _I, _I, _D, _IP, _I, _P, _I, _I, _D, _I, _I, _I, _P],
     "hhsr_divide": [_P, _P, _Z, _P],
     "hhsr_add_f64_f32": [_P, _P, _Z, _P],
+    "hhsr_add_many_f64_f32": [_P, C.POINTER(_P), _I, _Z, _P],
 }
 
 _lib = None

@@ -12,7 +12,7 @@ from .kernels import estimate_kernels
 from .merge import merge, merge_batch, merge_ref
 from .params import sanitize_config, update_snr_config
 from .robustness import compute_robustness, init_robustness
-from .utils import divide, timer
+from .utils import add_many, divide, timer
 from .utils_image import compute_grey_images
 
 
@@ -84,6 +84,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
         pending[i] = (t, ev)
 
     ids = list(ids)
+    r_maps = []
     if ids:
         prefetch(ids[0])
     for k, im_id in enumerate(ids):
@@ -96,13 +97,17 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
         if debug_mode:
             debug_dict["flow"].append(flow.cpu().numpy())
         r = compute_robustness_(cuda_img, ref_local_means, ref_local_stds, flow, cfa_pattern, white_balance,
-                                noise_tab, config, acc_rob=accumulated_r if config.robustness.enabled else None)
-        if accumulate_r and not config.robustness.enabled:
-            accumulated_r += r
+                                noise_tab, config)
+        if accumulate_r:
+            r_maps.append(r)      # accumulated_r += r (super_resolution.py:159), summed in frame order after the loop
         covs = estimate_kernels_(cuda_img, config)
         merge_(cuda_img, flow, covs, r, num, den, cfa_pattern, config)
         if debug_mode:
             debug_dict["robustness"].append(r.cpu().numpy())
+
+    if accumulate_r:
+        add_many(accumulated_r, r_maps)
+        r_maps = []
 
     # the one reduction point of the pipeline (frame-sharded runs): reduce_fn sums the accumulators across ranks and
     # may hand back the slice of output rows this rank has to normalise plus a callable that re-assembles the image

@@ -27,6 +27,17 @@ def add(A, B):
     _lib.call("hhsr_add_f64_f32", _lib.ptr(A), _lib.ptr(B), A.numel(), _lib.stream())
 
 
+def add_many(A, Bs):
+    """A (float64) += B_0 + B_1 + ... (float32, list order) in one pass over A — the per-frame `add(accumulated_r, r)`
+    of super_resolution.py:159 deferred to the end of the frame loop (same float64 sums, 1/K of the traffic on A)."""
+    import ctypes as C
+    assert A.dtype == torch.float64 and all(b.dtype == torch.float32 and b.shape == A.shape for b in Bs)
+    if not Bs:
+        return
+    arr = (C.c_void_p * len(Bs))(*[b.data_ptr() for b in Bs])
+    _lib.call("hhsr_add_many_f64_f32", _lib.ptr(A), arr, len(Bs), A.numel(), _lib.stream())
+
+
 def getTime(currentTime, labelName, printTime=True, spaceSize=50):
     """utils.py:26-30."""
     if printTime:

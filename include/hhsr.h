@@ -133,6 +133,8 @@ int hhsr_merge_ref(const float *raw, int H, int W, const float *covs, float *num
 /* ---- element-wise helpers (utils.py:62-120) */
 int hhsr_divide(float *num, const float *den, size_t n, hhsr_stream_t stream);
 int hhsr_add_f64_f32(double *A, const float *B, size_t n, hhsr_stream_t stream);
+/* A += B_0 + ... + B_{K-1} in list order, one pass over A (Bs: HOST array of K device pointers). */
+int hhsr_add_many_f64_f32(double *A, const float *const *Bs, int K, size_t n, hhsr_stream_t stream);
 
 #ifdef __cplusplus
 }
