@@ -13,12 +13,18 @@
 // sub-pixel position is formed exactly as the reference does it (float64: (hr+0.5)/scale + flow, truncation),
 // then reduced to tap-relative float32 offsets; weights are float32 with ex2.approx.  merge_ref runs once per
 // burst and keeps the reference's float64 arithmetic literally.
+// Compiled with -fmad=false (csrc/Makefile): every fused multiply-add in this file is written explicitly, so the
+// generic, fast-path and batched kernels round identically (bit-equal results) whatever the inlining context.
 #include "common.cuh"
+#include <cstdlib>
 
 // tuning knobs (see profiles/): resident CTAs per SM the register allocator must allow, and whether a thread keeps
 // the four covariance quads of its previous pixel in registers
 #ifndef HHSR_MERGE_MINBLOCKS
 #define HHSR_MERGE_MINBLOCKS 5
+#endif
+#ifndef HHSR_MERGE_POW2_MINBLOCKS
+#define HHSR_MERGE_POW2_MINBLOCKS 4
 #endif
 #ifndef HHSR_MERGE_REUSE_QUADS
 #define HHSR_MERGE_REUSE_QUADS 0
@@ -107,10 +113,10 @@ __device__ __forceinline__ void cov_coord(int c, float t, int n, int &i0, int &i
         fr = 0.5f * t;
     } else if (c > 0) {
         i0 = (c >> 1) - 1;
-        fr = 0.5f + 0.5f * t;
+        fr = fmaf(0.5f, t, 0.5f);
     } else {
         i0 = 0;
-        fr = 0.5f * t - 0.5f;
+        fr = fmaf(0.5f, t, -0.5f);
     }
     i1 = min(i0 + 1, n - 1);
 }
@@ -119,9 +125,8 @@ __device__ __forceinline__ void cov_coord(int c, float t, int n, int &i0, int &i
 // so the accumulation indices are compile-time; the CFA channel of each partial is resolved once at the end.
 // CHECK=false is the interior fast path (all 9 taps inside the frame, no per-tap tests).
 template <bool CHECK>
-__device__ __forceinline__ void merge_taps(const float *__restrict__ raw, int H, int W, int ci, int cj, float tx, float ty,
+__device__ __forceinline__ void merge_taps(const float *__restrict__ pc, int H, int W, int ci, int cj, float tx, float ty,
                                            float qxx, float qxy, float qyy, float (&v)[2][2], float (&a)[2][2]) {
-    const float *pc = raw + ((unsigned)max(ci, 0) * (unsigned)W + (unsigned)max(cj, 0));
 #pragma unroll
     for (int di = -1; di <= 1; ++di) {
         if (CHECK && (ci + di < 0 || ci + di >= H)) continue;
@@ -133,7 +138,7 @@ __device__ __forceinline__ void merge_taps(const float *__restrict__ raw, int H,
             if (CHECK && (cj + dj < 0 || cj + dj >= W)) continue;
             const float c = __ldg(row + dj);
             const float dx = (float)dj + 0.5f - tx;
-            float z = (qxx * dx + qm) * dx + qy;
+            float z = fmaf(fmaf(qxx, dx, qm), dx, qy);
             z = fminf(0.0f, z);               // == -0.5*log2e*max(0, z_ref); NaN -> 0
             const float w = ex2_approx(z);
             v[di & 1][dj & 1] = fmaf(w, c, v[di & 1][dj & 1]);
@@ -142,11 +147,10 @@ __device__ __forceinline__ void merge_taps(const float *__restrict__ raw, int H,
     }
 }
 
-// Fold the four parity partials into the three colour channels, scaled by the robustness r:
-// out = r * sum (ACCUM: out += r * sum).  Bayer patterns take 7 selects; anything else the generic 12.
-template <bool ACCUM>
-__device__ __forceinline__ void resolve_channels(const CfaInfo &cf, int ci, int cj, float r, const float (&v)[2][2],
-                                                 float (&out)[3]) {
+// Fold the four parity partials into the three colour channels (unscaled: every kernel applies the robustness as
+// acc = fmaf(r, sum, acc), one rounding, so single-frame, batched and fast-path launches agree bit for bit).
+// Bayer patterns take 7 selects; anything else the generic 12.
+__device__ __forceinline__ void resolve_channels(const CfaInfo &cf, int ci, int cj, const float (&v)[2][2], float (&out)[3]) {
     float ch[3];
     if (cf.bayer) {
         // rel main diagonal == abs main diagonal iff ci and cj have equal parity
@@ -175,7 +179,7 @@ __device__ __forceinline__ void resolve_channels(const CfaInfo &cf, int ci, int 
             }
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) out[k] = ACCUM ? fmaf(r, ch[k], out[k]) : r * ch[k];
+    for (int k = 0; k < 3; ++k) out[k] = ch[k];
 }
 
 // Interpolated covariance -> pre-scaled inverse quadratic form.  w = exp(-z/2) = 2^(qxx dx^2 + qxy dx dy + qyy dy^2)
@@ -184,9 +188,25 @@ struct CovQuads {
     float4 tr, tl, br, bl;
 };
 
-template <bool ISO, bool ACCUM>
+// bilinear blend of the four covariance quads (x first, then y; merge.py:365-389) and its pre-scaled inverse
+__device__ __forceinline__ void cov_form(const float4 &tr, const float4 &tl, const float4 &br, const float4 &bl, float frx,
+                                         float fry, float &qxx, float &qxy, float &qyy) {
+    const float kS = -0.72134752044448170368f;   // -0.5 * log2(e)
+    const float top_xx = fmaf(frx, tl.x - tr.x, tr.x), bot_xx = fmaf(frx, bl.x - br.x, br.x);
+    const float top_xy = fmaf(frx, tl.y - tr.y, tr.y), bot_xy = fmaf(frx, bl.y - br.y, br.y);
+    const float top_yy = fmaf(frx, tl.w - tr.w, tr.w), bot_yy = fmaf(frx, bl.w - br.w, br.w);
+    const float cxx = fmaf(fry, bot_xx - top_xx, top_xx);
+    const float cxy = fmaf(fry, bot_xy - top_xy, top_xy);
+    const float cyy = fmaf(fry, bot_yy - top_yy, top_yy);
+    const float inv_det = __fdividef(kS, fmaf(cxx, cyy, -(cxy * cxy)));      // merge.py:391-396
+    qxx = inv_det * cyy;
+    qxy = -2.0f * inv_det * cxy;
+    qyy = inv_det * cxx;
+}
+
+template <bool ISO>
 __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom &g, int cj, float tx, int ci, float ty,
-                                            float local_r, CovQuads &cq, float (&val)[3], float (&acc)[3]) {
+                                            CovQuads &cq, float (&val)[3], float (&acc)[3]) {
     const float kS = -0.72134752044448170368f;   // -0.5 * log2(e)
     float qxx, qxy, qyy;
     if (ISO) {
@@ -203,25 +223,18 @@ __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom
             cq.tr = __ldg(r0 + fx0), cq.tl = __ldg(r0 + cx1), cq.br = __ldg(r1 + fx0), cq.bl = __ldg(r1 + cx1);
             cq.fx0 = fx0, cq.fy0 = fy0;
         }
-        const float top_xx = cq.tr.x + frx * (cq.tl.x - cq.tr.x), bot_xx = cq.br.x + frx * (cq.bl.x - cq.br.x);
-        const float top_xy = cq.tr.y + frx * (cq.tl.y - cq.tr.y), bot_xy = cq.br.y + frx * (cq.bl.y - cq.br.y);
-        const float top_yy = cq.tr.w + frx * (cq.tl.w - cq.tr.w), bot_yy = cq.br.w + frx * (cq.bl.w - cq.br.w);
-        const float cxx = top_xx + fry * (bot_xx - top_xx);
-        const float cxy = top_xy + fry * (bot_xy - top_xy);
-        const float cyy = top_yy + fry * (bot_yy - top_yy);
-        const float inv_det = __fdividef(kS, cxx * cyy - cxy * cxy);             // merge.py:391-396
-        qxx = inv_det * cyy;
-        qxy = -2.0f * inv_det * cxy;
-        qyy = inv_det * cxx;
+        cov_form(cq.tr, cq.tl, cq.br, cq.bl, frx, fry, qxx, qxy, qyy);
     }
     float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, a[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    const float *pc = f.raw + ((unsigned)max(ci, 0) * (unsigned)g.W + (unsigned)max(cj, 0));
     if (ci >= 1 && ci <= g.H - 2 && cj >= 1 && cj <= g.W - 2)
-        merge_taps<false>(f.raw, g.H, g.W, ci, cj, tx, ty, qxx, qxy, qyy, v, a);
+        merge_taps<false>(pc, g.H, g.W, ci, cj, tx, ty, qxx, qxy, qyy, v, a);
     else
-        merge_taps<true>(f.raw, g.H, g.W, ci, cj, tx, ty, qxx, qxy, qyy, v, a);
-    // the reference multiplies every tap weight by r (merge.py:430-431); factored out here (float32 rounding level)
-    resolve_channels<ACCUM>(g.cfa, ci, cj, local_r, v, val);
-    resolve_channels<ACCUM>(g.cfa, ci, cj, local_r, a, acc);
+        merge_taps<true>(pc, g.H, g.W, ci, cj, tx, ty, qxx, qxy, qyy, v, a);
+    // the reference multiplies every tap weight by r (merge.py:430-431); factored out (float32 rounding level) and
+    // applied by the caller
+    resolve_channels(g.cfa, ci, cj, v, val);
+    resolve_channels(g.cfa, ci, cj, a, acc);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -241,9 +254,10 @@ struct RowCtx {
     bool ok_y;
 };
 
-template <bool ISO, bool ACCUM>
-__device__ __forceinline__ void merge_hr_pixel(const MergeFrame &f, const MergeGeom &g, int hr_j, RowCtx &rc, CovQuads &cq,
-                                               float (&val)[3], float (&acc)[3]) {
+// val/acc: unscaled channel sums of this pixel; returns its robustness r (0 with val = acc = 0 when the pixel is skipped)
+template <bool ISO>
+__device__ __forceinline__ float merge_hr_pixel(const MergeFrame &f, const MergeGeom &g, int hr_j, RowCtx &rc, CovQuads &cq,
+                                                float (&val)[3], float (&acc)[3]) {
     const double lr_x = lr_coord(hr_j, g.scale, g.inv_scale, g.pow2);
     const int ilx = (int)lr_x;
     const int tcol = tile_of(ilx, g);
@@ -254,9 +268,10 @@ __device__ __forceinline__ void merge_hr_pixel(const MergeFrame &f, const MergeG
     }
     int cj;
     float tx;
-    if (!rc.ok_y || !split_pos(lr_x, rc.fl.x, g.W, cj, tx)) return;
+    if (!rc.ok_y || !split_pos(lr_x, rc.fl.x, g.W, cj, tx)) return 0.0f;
     const float local_r = __ldg(f.r + (unsigned)rc.i_r * (unsigned)g.W + (unsigned)min(ilx, g.W - 1));
-    merge_pixel<ISO, ACCUM>(f, g, cj, tx, rc.ci, rc.ty, local_r, cq, val, acc);
+    merge_pixel<ISO>(f, g, cj, tx, rc.ci, rc.ty, cq, val, acc);
+    return local_r;
 }
 
 // Single comp frame (the reference's launch granularity, merge.py:284-287).  One thread = VEC consecutive HR pixels
@@ -264,20 +279,11 @@ __device__ __forceinline__ void merge_hr_pixel(const MergeFrame &f, const MergeG
 // gathers/weights are done: its registers are not live during the math (more resident warps) while its HBM latency
 // still overlaps the math.  `num += val` with val the per-frame sum, exactly as the reference.
 template <bool ISO, int VEC>
-__global__ void __launch_bounds__(256, HHSR_MERGE_MINBLOCKS) accumulate_kernel(MergeFrame f, MergeGeom g, float *__restrict__ num,
-                                                                                float *__restrict__ den) {
-    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
-    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (hr_i >= g.Hs || j0 >= g.Ws) return;
+__device__ __forceinline__ void accumulate_thread(const MergeFrame &f, const MergeGeom &g, float *__restrict__ num,
+                                                  float *__restrict__ den, int hr_i, int j0) {
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
     const bool full = (VEC == 4) && (j0 + VEC <= g.Ws);
-    if (VEC == 4 && (threadIdx.x & 1) == 0) {   // 2 threads share 96 B = at most 2 lines per accumulator
-        prefetch_l2(num + base);
-        prefetch_l2(den + base);
-        prefetch_l2(num + base + 23);
-        prefetch_l2(den + base + 23);
-    }
-    float n[VEC][3], d[VEC][3];
+    float n[VEC][3], d[VEC][3], rr[VEC];
     RowCtx rc;
     rc.lr_y = lr_coord(hr_i, g.scale, g.inv_scale, g.pow2);                     // merge.py:319-320
     const int ily = (int)rc.lr_y;
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_MINBLOCKS) accumulate_kernel(M
 #pragma unroll
     for (int p = 0; p < VEC; ++p) {
         n[p][0] = n[p][1] = n[p][2] = d[p][0] = d[p][1] = d[p][2] = 0.f;
-        if (j0 + p < g.Ws) merge_hr_pixel<ISO, false>(f, g, j0 + p, rc, cq, n[p], d[p]);
+        rr[p] = (j0 + p < g.Ws) ? merge_hr_pixel<ISO>(f, g, j0 + p, rc, cq, n[p], d[p]) : 0.0f;
     }
     if (full) {
         const float *nf = &n[0][0], *df = &d[0][0];
@@ -296,8 +302,10 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_MINBLOCKS) accumulate_kernel(M
         for (int q = 0; q < 3; ++q) {
             float4 a = *reinterpret_cast<const float4 *>(num + base + 4 * q);
             float4 c = *reinterpret_cast<const float4 *>(den + base + 4 * q);
-            a.x += nf[4 * q], a.y += nf[4 * q + 1], a.z += nf[4 * q + 2], a.w += nf[4 * q + 3];
-            c.x += df[4 * q], c.y += df[4 * q + 1], c.z += df[4 * q + 2], c.w += df[4 * q + 3];
+            a.x = fmaf(rr[(4 * q) / 3], nf[4 * q], a.x), a.y = fmaf(rr[(4 * q + 1) / 3], nf[4 * q + 1], a.y);
+            a.z = fmaf(rr[(4 * q + 2) / 3], nf[4 * q + 2], a.z), a.w = fmaf(rr[(4 * q + 3) / 3], nf[4 * q + 3], a.w);
+            c.x = fmaf(rr[(4 * q) / 3], df[4 * q], c.x), c.y = fmaf(rr[(4 * q + 1) / 3], df[4 * q + 1], c.y);
+            c.z = fmaf(rr[(4 * q + 2) / 3], df[4 * q + 2], c.z), c.w = fmaf(rr[(4 * q + 3) / 3], df[4 * q + 3], c.w);
             *reinterpret_cast<float4 *>(num + base + 4 * q) = a;
             *reinterpret_cast<float4 *>(den + base + 4 * q) = c;
         }
@@ -307,9 +315,178 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_MINBLOCKS) accumulate_kernel(M
             if (j0 + p < g.Ws)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    num[base + p * 3 + c] += n[p][c];
-                    den[base + p * 3 + c] += d[p][c];
+                    num[base + p * 3 + c] = fmaf(rr[p], n[p][c], num[base + p * 3 + c]);
+                    den[base + p * 3 + c] = fmaf(rr[p], d[p][c], den[base + p * 3 + c]);
                 }
+    }
+}
+
+template <bool ISO, int VEC>
+__global__ void __launch_bounds__(256, HHSR_MERGE_MINBLOCKS) accumulate_kernel(MergeFrame f, MergeGeom g, float *__restrict__ num,
+                                                                                float *__restrict__ den) {
+    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (hr_i >= g.Hs || j0 >= g.Ws) return;
+    if (VEC == 4 && (threadIdx.x & 1) == 0) {   // 2 threads share 96 B = at most 2 lines per accumulator
+        const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
+        prefetch_l2(num + base);
+        prefetch_l2(den + base);
+        prefetch_l2(num + base + 23);
+        prefetch_l2(den + base + 23);
+    }
+    accumulate_thread<ISO, VEC>(f, g, num, den, hr_i, j0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast path for scale = 2^K (K = 0, 1, 2: scales 1, 2, 4), Ws % 4 == 0 and a power-of-two tile size >= 4.
+// (hr + 0.5) / 2^K = ((2 hr + 1) >> (K+1)) + q with q = ((2 hr + 1) mod 2^(K+1)) / 2^(K+1) a short dyadic fraction, so
+// the reference's float64 position  m = lr + flow  splits EXACTLY without float64:  flow = fi + ff (trunc / signed
+// fraction, exact in float32),  floor(m) = base + fi + l  with  l = floor(q + ff) in {-1, 0, 1} decided by exact
+// comparisons of ff against 1 - q and -q,  and the fraction  t = (q - l) + ff  is one correctly rounded float32 add of
+// exactly representable terms — the same value as the reference's float32(m - trunc(m)).  The four pixels of a thread
+// share the row, the flow tile and (for K = 1) two x-splits; row pointers, covariance rows and the y-split are
+// formed once per thread.  Threads whose 3x3 windows touch the frame border (or leave the frame) take the generic
+// per-pixel code, so results are identical to accumulate_kernel.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_q(float q, float ff, int &l, float &t) {
+    l = (ff >= 1.0f - q) ? 1 : ((ff < -q) ? -1 : 0);
+    t = (q - (float)l) + ff;
+}
+
+template <bool ISO>
+__device__ __noinline__ void accumulate_thread_border(const MergeFrame *f, const MergeGeom *g, float *num, float *den, int hr_i,
+                                                      int j0) {
+    accumulate_thread<ISO, 4>(*f, *g, num, den, hr_i, j0);
+}
+
+// p[0..3] = fmaf(r_k, x_k, p[0..3])
+__device__ __forceinline__ void rmw4(float *__restrict__ p, float r0, float a, float r1, float b, float r2, float c, float r3,
+                                     float d) {
+    float4 v = *reinterpret_cast<const float4 *>(p);
+    v.x = fmaf(r0, a, v.x), v.y = fmaf(r1, b, v.y), v.z = fmaf(r2, c, v.z), v.w = fmaf(r3, d, v.w);
+    *reinterpret_cast<float4 *>(p) = v;
+}
+
+// Interior 3x3 taps addressed by a 32-bit element offset `o` of the centre tap (one IMAD.WIDE per row, immediates
+// for the columns); same arithmetic and order as merge_taps<false>.
+__device__ __forceinline__ void merge_taps_off(const float *__restrict__ raw, int W, int o, float tx, float ty, float qxx,
+                                               float qxy, float qyy, float (&v)[2][2], float (&a)[2][2]) {
+#pragma unroll
+    for (int di = -1; di <= 1; ++di) {
+        const float dy = (float)di + 0.5f - ty;
+        const float qy = qyy * dy * dy, qm = qxy * dy;
+        const float *row = raw + (o + di * W);
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) {
+            const float c = __ldg(row + dj);
+            const float dx = (float)dj + 0.5f - tx;
+            float z = fmaf(fmaf(qxx, dx, qm), dx, qy);
+            z = fminf(0.0f, z);
+            const float w = ex2_approx(z);
+            v[di & 1][dj & 1] = fmaf(w, c, v[di & 1][dj & 1]);
+            a[di & 1][dj & 1] += w;
+        }
+    }
+}
+
+// Channel resolve for Bayer patterns with green = channel 1: the pattern is RGGB read at phase (py0, px0), so with
+// sy = (ci + py0) & 1, sx = (cj + px0) & 1 the relative-parity partial v[ry][rx] sits at RGGB position (ry^sy, rx^sx):
+// R = v[sy][sx], B = v[!sy][!sx], G = v[sy][!sx] + v[!sy][sx] (first-row + second-row partial, like resolve_channels).
+__device__ __forceinline__ void resolve_rggb(bool sy, bool sx, const float (&v)[2][2], float (&out)[3]) {
+    const float t0 = sy ? v[1][0] : v[0][0], t1 = sy ? v[1][1] : v[0][1];   // RGGB row 0 (R G)
+    const float b0 = sy ? v[0][0] : v[1][0], b1 = sy ? v[0][1] : v[1][1];   // RGGB row 1 (G B)
+    const float R = sx ? t1 : t0, Gt = sx ? t0 : t1, Gb = sx ? b1 : b0, B = sx ? b0 : b1;
+    const float G = sy ? (Gb + Gt) : (Gt + Gb);                             // rel row 0 partial first
+    out[0] = R, out[1] = G, out[2] = B;
+}
+
+template <bool ISO, int K>
+__global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_kernel(const __grid_constant__ MergeFrame f,
+                                                                                     const __grid_constant__ MergeGeom g,
+                                                                                     float *__restrict__ num,
+                                                                                     float *__restrict__ den) {
+    constexpr int SH = K + 1, MASK = (1 << SH) - 1;
+    constexpr float INV = 1.0f / (float)(1 << SH);
+    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (hr_i >= g.Hs || j0 >= g.Ws) return;
+    const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
+    if ((threadIdx.x & 1) == 0) {
+        prefetch_l2(num + base);
+        prefetch_l2(den + base);
+        prefetch_l2(num + base + 23);
+        prefetch_l2(den + base + 23);
+    }
+    const int W = g.W, cw = g.cw;
+    // y split (shared by the four pixels)
+    const int n2 = 2 * hr_i + 1;
+    const int by = n2 >> SH;                                   // int(lr_y) <= H - 1
+    const float qy = (float)(n2 & MASK) * INV;
+    const int bx0 = j0 >> K;                                   // int(lr_x) of pixel 0; all four pixels lie in one tile
+    const float2 fl = __ldg(reinterpret_cast<const float2 *>(f.flow) + ((by >> g.ts_shift) * g.nx + (bx0 >> g.ts_shift)));
+    const float fiy = truncf(fl.y), fix = truncf(fl.x);
+    const float ffy = fl.y - fiy, ffx = fl.x - fix;
+    int ly;
+    float ty;
+    split_q(qy, ffy, ly, ty);
+    const int ci = by + (int)fiy + ly;
+    const int bx = bx0 + (int)fix;
+    int cj[4];
+    float tx[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int bp = (2 * p + 1) >> SH;
+        const float qp = (float)((2 * p + 1) & MASK) * INV;
+        int lx;
+        split_q(qp, ffx, lx, tx[p]);
+        cj[p] = bx + bp + lx;
+    }
+    // every 3x3 window strictly inside the frame (cj is non-decreasing in p) and a green-is-1 Bayer pattern?
+    if (!(ci >= 1 && ci <= g.H - 2 && cj[0] >= 1 && cj[3] <= W - 2 && g.cfa.bayer && g.cfa.dup == 1)) {
+        accumulate_thread_border<ISO>(&f, &g, num, den, hr_i, j0);
+        return;
+    }
+    // RGGB phase of the pattern: (py0, px0) = position of channel 0 ... pattern(y, x) = RGGB(y + py0, x + px0)
+    const int red_at = ((g.cfa.packed & 3) == 0) ? 0 : (((g.cfa.packed >> 2) & 3) == 0) ? 1 : (((g.cfa.packed >> 4) & 3) == 0) ? 2 : 3;
+    const bool sy = ((ci + (red_at >> 1)) & 1) != 0;
+    const int px0 = red_at & 1;
+    const int orow = ci * W;
+    const float *rrow = f.r + (by * W + bx0);
+    // covariance rows: inside the frame interior k = m/2 - 0.5 has i0 = (c - 1) >> 1, i1 = i0 + 1 (no clamping) and
+    // fraction t/2 (+ 1/2 for even c) — cov_coord() without its border cases
+    const int oqy = ((ci - 1) >> 1) * cw;
+    const float fry = fmaf(0.5f, ty, (ci & 1) ? 0.0f : 0.5f);
+    const float4 *c4 = reinterpret_cast<const float4 *>(f.covs);
+    float n[12], d[12], rr[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int bp = (2 * p + 1) >> SH;
+        float qxx, qxy, qyy;
+        if (ISO) {
+            qxx = qyy = 2.0f * -0.72134752044448170368f, qxy = 0.0f;
+        } else {
+            const float4 *q0 = c4 + (oqy + ((cj[p] - 1) >> 1));
+            const float4 *q1 = c4 + (oqy + cw + ((cj[p] - 1) >> 1));
+            const float frx = fmaf(0.5f, tx[p], (cj[p] & 1) ? 0.0f : 0.5f);
+            const float4 tr = __ldg(q0), tl = __ldg(q0 + 1), br = __ldg(q1), bl = __ldg(q1 + 1);
+            cov_form(tr, tl, br, bl, frx, fry, qxx, qxy, qyy);
+        }
+        float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, a[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        merge_taps_off(f.raw, W, orow + cj[p], tx[p], ty, qxx, qxy, qyy, v, a);
+        rr[p] = __ldg(rrow + bp);
+        const bool sx = ((cj[p] + px0) & 1) != 0;
+        float val[3], acc[3];
+        resolve_rggb(sy, sx, v, val);
+        resolve_rggb(sy, sx, a, acc);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) n[3 * p + c] = val[c], d[3 * p + c] = acc[c];
+        if (p >= 1) {   // float4 number p-1 of the 12-float slice is complete
+            const int q = p - 1;
+            rmw4(num + base + 4 * q, rr[(4 * q) / 3], n[4 * q], rr[(4 * q + 1) / 3], n[4 * q + 1], rr[(4 * q + 2) / 3],
+                 n[4 * q + 2], rr[(4 * q + 3) / 3], n[4 * q + 3]);
+            rmw4(den + base + 4 * q, rr[(4 * q) / 3], d[4 * q], rr[(4 * q + 1) / 3], d[4 * q + 1], rr[(4 * q + 2) / 3],
+                 d[4 * q + 2], rr[(4 * q + 3) / 3], d[4 * q + 3]);
+        }
     }
 }
 
@@ -352,11 +529,11 @@ __global__ void __launch_bounds__(256, 2) accumulate_batch_kernel(MergeBatch b, 
         for (int p = 0; p < VEC; ++p) {
             if (j0 + p >= g.Ws) break;
             float val[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
-            merge_hr_pixel<ISO, false>(b.f[k], g, j0 + p, rc, cq, val, acc);
+            const float rl = merge_hr_pixel<ISO>(b.f[k], g, j0 + p, rc, cq, val, acc);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                n[p * 3 + c] += val[c];
-                d[p * 3 + c] += acc[c];
+                n[p * 3 + c] = fmaf(rl, val[c], n[p * 3 + c]);
+                d[p * 3 + c] = fmaf(rl, acc[c], d[p * 3 + c]);
             }
         }
     }
@@ -405,10 +582,10 @@ __global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__rest
         const float4 c00 = __ldg(c4 + (unsigned)fy0 * (unsigned)g.cw + fx0), c01 = __ldg(c4 + (unsigned)fy0 * (unsigned)g.cw + cx1);
         const float4 c10 = __ldg(c4 + (unsigned)cy1 * (unsigned)g.cw + fx0), c11 = __ldg(c4 + (unsigned)cy1 * (unsigned)g.cw + cx1);
         const float w00 = (1.f - rx) * (1.f - ry), w01 = rx * (1.f - ry), w10 = (1.f - rx) * ry, w11 = rx * ry;
-        const float m00 = c00.x * w00 + c01.x * w01 + c10.x * w10 + c11.x * w11;
-        const float m01 = c00.y * w00 + c01.y * w01 + c10.y * w10 + c11.y * w11;
-        const float m10 = c00.z * w00 + c01.z * w01 + c10.z * w10 + c11.z * w11;
-        const float m11 = c00.w * w00 + c01.w * w01 + c10.w * w10 + c11.w * w11;
+        const float m00 = fmaf(c11.x, w11, fmaf(c10.x, w10, fmaf(c01.x, w01, c00.x * w00)));
+        const float m01 = fmaf(c11.y, w11, fmaf(c10.y, w10, fmaf(c01.y, w01, c00.y * w00)));
+        const float m10 = fmaf(c11.z, w11, fmaf(c10.z, w10, fmaf(c01.z, w01, c00.z * w00)));
+        const float m11 = fmaf(c11.w, w11, fmaf(c10.w, w10, fmaf(c01.w, w01, c00.w * w00)));
         const float det = __fmaf_rn(m00, m11, -__fmul_rn(m01, m10));                             // linalg.py:53
         float i00 = 1.f, i0110 = 0.f, i11 = 1.f;
         if (fabsf(det) > 1e-10f) {                                                               // EPSILON_DIV
@@ -442,7 +619,7 @@ __global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__rest
             const int chn = cfa_channel(g.cfa.packed, yy, xx);
             const float c = __ldg(raw + (unsigned)yy * (unsigned)g.W + xx);
             const float dx = (float)xx - pos_x;
-            const float z = fminf(0.f, (qxx * dx + qm) * dx + qy);                               // max(0, y): NaN -> 0
+            const float z = fminf(0.f, fmaf(fmaf(qxx, dx, qm), dx, qy));                         // max(0, y): NaN -> 0
             // The reference's float32 accumulators keep weights down to the subnormal range (1e-45) and a channel
             // fed only by far taps of a narrow kernel is normalised from exactly those: evaluate them in float64.
             const float w = (z > -120.f) ? ex2_approx(z) : (float)exp2((double)z);
@@ -523,9 +700,36 @@ static void launch_accumulate_vec(const MergeBatch &b, const MergeGeom &g, float
     }
 }
 
+// scale 1, 2 or 4 with the geometry the fast path assumes; HHSR_MERGE_GENERIC=1 forces the generic kernel (A/B tests)
+static int pow2_fast_shift(const MergeGeom &g) {
+    const char *e = std::getenv("HHSR_MERGE_GENERIC");
+    const bool force_generic = e && e[0] == '1';
+    if (force_generic || !g.pow2 || g.ts_shift < 2 || g.Ws % 4 != 0) return -1;
+    for (int k = 0; k <= 2; ++k)
+        if (g.scale == (double)(1 << k) && g.Hs == (g.H << k) && g.Ws == (g.W << k)) return k;
+    return -1;
+}
+
+template <int K>
+static void launch_pow2(const MergeFrame &f, const MergeGeom &g, float *num, float *den, int iso, dim3 grid, dim3 block,
+                        cudaStream_t st) {
+    if (iso)
+        accumulate_pow2_kernel<true, K><<<grid, block, 0, st>>>(f, g, num, den);
+    else
+        accumulate_pow2_kernel<false, K><<<grid, block, 0, st>>>(f, g, num, den);
+}
+
 static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso,
                              cudaStream_t st) {
     dim3 block(32, 8);
+    const int k = b.K == 1 ? pow2_fast_shift(g) : -1;
+    if (k >= 0) {
+        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8));
+        if (k == 0) launch_pow2<0>(b.f[0], g, num, den, iso, grid, block, st);
+        if (k == 1) launch_pow2<1>(b.f[0], g, num, den, iso, grid, block, st);
+        if (k == 2) launch_pow2<2>(b.f[0], g, num, den, iso, grid, block, st);
+        return launch_status("merge_accumulate");
+    }
     if (g.Ws % 4 == 0)
         launch_accumulate_vec<4>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8)), block, st);
     else

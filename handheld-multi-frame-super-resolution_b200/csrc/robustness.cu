@@ -10,6 +10,7 @@
 // Arithmetic follows the compiled reference: float64 wherever Numba promotes (white-balance division, Dodgson
 // weights, noise-model shrinkage, the final S*exp - t), float32 sums where the reference keeps float32 arrays.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace hhsr {
 
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(RBX *RBY) upscale_warp_kernel(const float *__r
 
 struct RobParams {
     double t, s1, s2, Mt;
-    int n_curve;
+    int force_generic;
 };
 
 // flow irregularity of tile (py, px): s1 if the range of the flow over the 3x3 tile neighbourhood exceeds Mt
@@ -219,103 +220,217 @@ __global__ void noise_table_kernel(const double *__restrict__ std_curve, const d
     if (i < n) table[i] = make_float2((float)(std_curve[i] * std_curve[i]), (float)(diff_curve[i] * diff_curve[i]));
 }
 
+// Reference-side noise terms, once per burst: everything of cuda_apply_noise_model (robustness.py:504-533) that
+// depends on the reference statistics only.  terms[c] = d_t^2 of the brightness level of channel c (c = 0..2),
+// terms[3] = sum_c max(sigma_p^2, sigma_t^2) accumulated in channel order in float32.
+__global__ void ref_noise_terms_kernel(const float *__restrict__ ref_means, const float *__restrict__ ref_vars, size_t plane,
+                                       const float2 *__restrict__ table, int n_curve, float *__restrict__ terms) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < plane; o += stride) {
+        float sigma_sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float brightness = ref_means[o + c * plane];
+            int id = 0;
+            if (isfinite(brightness)) id = (int)llrint(1000.0 * (double)brightness);   // robustness.py:519 (float64 product)
+            id = min(max(id, 0), n_curve - 1);
+            const float2 t = __ldg(table + id);
+            sigma_sq += fmaxf(ref_vars[o + c * plane], t.x);                           // max(sigma_p^2, sigma_t^2), :524
+            terms[o + c * plane] = t.y;
+        }
+        terms[o + 3 * plane] = sigma_sq;
+    }
+}
+
 // Noise model + threshold for one pixel given its warped comp means (robustness.py:452-462, 504-533, 626-639)
-__device__ __forceinline__ float robustness_value(const float (&cm)[3], float rm0, const float *__restrict__ ref_means,
-                                                  const float *__restrict__ ref_vars, unsigned o, unsigned plane,
-                                                  const float2 *__restrict__ table, const RobParams &p, float S) {
-    float sigma_sq = 0.f, d_sq = 0.f;
+__device__ __forceinline__ float robustness_finish(float d_sq, float sigma_sq, float S, double t) {
+    const float e = expf(-__fdividef(d_sq, sigma_sq));                      // math.exp(float32), :638
+    const float v = (float)((double)(S * e) - t);
+    return fminf(1.f, fmaxf(0.f, v));                                       // NaN -> 0
+}
+__device__ __forceinline__ float shrunk_dist(float brightness, float comp, float dt_sq) {
+    const float d_p = fabsf(brightness - comp);                             // :462
+    const float d_p_sq = d_p * d_p;
+    const float shrink = __fdividef(d_p_sq, d_p_sq + dt_sq);
+    return d_p_sq * shrink * shrink;
+}
+
+// Generic per-pixel path (any tile size, frame borders): Dodgson axes per pixel.
+__device__ __forceinline__ float robustness_pixel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
+                                                  const float *__restrict__ terms, int H, int W, int x, int y, const Axis &ay,
+                                                  const Axis &ax, float S, double t) {
+    const int h = H / 2, w = W / 2;
+    const unsigned plane = (unsigned)H * (unsigned)W, lplane = (unsigned)h * (unsigned)w, o = (unsigned)y * (unsigned)W + x;
+    const float rm0 = __ldg(ref_means + o);
+    if (!(ay.ok && ax.ok && isfinite(rm0))) return 0.f;   // any non-finite statistic ends as clamp(NaN) = 0
+    float buf[3] = {0.f, 0.f, 0.f}, wacc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float *row = comp_lr + (unsigned)ay.i[i] * (unsigned)w;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float wgt = ay.w[i] * ax.w[j];
+            const float *q = row + ax.i[j];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) buf[c] = fmaf(__ldg(q + c * lplane), wgt, buf[c]);
+            wacc += wgt;
+        }
+    }
+    const float inv_w = __fdividef(1.0f, wacc);
+    float d_sq = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float brightness = c == 0 ? rm0 : __ldg(ref_means + o + c * plane);
-        int id = (int)llrint(1000.0 * (double)brightness);                  // robustness.py:519 (float64 product)
-        id = min(max(id, 0), p.n_curve - 1);
-        const float2 t = __ldg(table + id);
-        const float sigma_p_sq = __ldg(ref_vars + o + c * plane);
-        sigma_sq += fmaxf(sigma_p_sq, t.x);                                 // max(sigma_p^2, sigma_t^2), :524
-        const float d_p = fabsf(brightness - cm[c]);                        // :462
-        const float d_p_sq = d_p * d_p;
-        const float shrink = __fdividef(d_p_sq, d_p_sq + t.y);
-        d_sq += d_p_sq * shrink * shrink;
+        d_sq += shrunk_dist(brightness, buf[c] * inv_w, __ldg(terms + o + c * plane));
     }
-    const float e = expf(-__fdividef(d_sq, sigma_sq));                      // math.exp(float32), :638
-    const float v = (float)((double)(S * e) - p.t);
-    return fminf(1.f, fmaxf(0.f, v));                                       // NaN -> 0
+    return robustness_finish(d_sq, __ldg(terms + o + 3 * plane), S, t);
 }
 
-// One thread per raw pixel.  When the tile size is a multiple of 32 a 32x8 block lies inside one flow tile: flow,
-// S and the Dodgson axes (8 row axes + 32 column axes instead of 2 per thread) are then computed once per block.
-__global__ void __launch_bounds__(RBX *RBY) robustness_kernel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
-                                                              const float *__restrict__ ref_vars, int H, int W,
+// One thread = 4 pixels x 2 rows; a 8x16-thread block covers 32x32 raw pixels.  When the tile size is a multiple of 32
+// the block lies inside one flow tile, and because the guide image is at half resolution the Dodgson tap weights
+// depend on the pixel only through the PARITY of (x + trunc(flow)): two weight sets per axis for the whole block.
+// The block prologue expands them to zero-padded per-pixel weight rows (5 columns for the 4 pixels, 4 rows for the
+// 2 rows of a thread), so a thread reads a 4x5 window of the comp guide means per channel (instead of 9 taps per
+// pixel) and blends it separably.  Blocks whose windows touch the guide border (clamped taps, +inf band) and
+// tile sizes that are not a multiple of 32 use the per-pixel path.
+constexpr int RTX = 8, RTY = 16;
+struct RobTile {
+    float wx[4][5], wy[2][4];
+    int dx0, dy0, fast;
+    float S;
+    float2 f;
+};
+
+// parity classes e = 0, 1 of T = coordinate + trunc(flow): offset of the 3-tap window start relative to T >> 1 and the
+// (normalised) weights.  v = 0.5 e + 0.5 u - 0.5 with u = 0.5 + frac(flow) (see dodgson_axis).
+__device__ __forceinline__ void parity_weights(float fl, int (&start)[2], float (&wgt)[2][3]) {
+    const float u = 0.5f + (fl - truncf(fl));
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const float v = 0.5f * (float)e + 0.5f * u - 0.5f;
+        const int off = (int)rintf(v);          // ties: the extra tap has weight q(1.5) = 0 either way
+        start[e] = off - 1;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            wgt[e][k] = dodgson_f((float)(off - 1 + k) - v);
+            sum += wgt[e][k];
+        }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) wgt[e][k] *= inv;
+    }
+}
+
+__global__ void __launch_bounds__(RTX *RTY) robustness_kernel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
+                                                              const float *__restrict__ terms, int H, int W,
                                                               const float *__restrict__ flow, int ny, int nx, int ts,
-                                                              const float2 *__restrict__ table, RobParams p,
-                                                              float *__restrict__ R) {
-    const int x = blockIdx.x * RBX + threadIdx.x, y = blockIdx.y * RBY + threadIdx.y;
+                                                              RobParams p, float *__restrict__ R) {
     const float2 *fl = reinterpret_cast<const float2 *>(flow);
     const int h = H / 2, w = W / 2;
-    __shared__ float s_S;
-    __shared__ Axis s_ay[RBY], s_ax[RBX];
-    const bool uniform = (ts % RBX) == 0;
-    Axis ay, ax;
-    float S;
+    const int xb = blockIdx.x * (RTX * 4), yb = blockIdx.y * (RTY * 2);
+    const int x0 = xb + threadIdx.x * 4, y0 = yb + threadIdx.y * 2;
+    __shared__ RobTile s;
+    const bool uniform = (ts % 32) == 0 && (W % 4) == 0 && !p.force_generic;
     if (uniform) {
-        const int tid = threadIdx.y * RBX + threadIdx.x;
-        const int py = (blockIdx.y * RBY) / ts, px = (blockIdx.x * RBX) / ts;
-        const float2 f = __ldg(fl + (size_t)py * nx + px);
-        if (tid < RBX)
-            s_ax[tid] = dodgson_axis(min(blockIdx.x * RBX + tid, W - 1), f.x, w);
-        else if (tid < RBX + RBY)
-            s_ay[tid - RBX] = dodgson_axis(min(blockIdx.y * RBY + tid - RBX, H - 1), f.y, h);
-        else if (tid == RBX + RBY)
-            s_S = tile_S(fl, py, px, ny, nx, p);
+        const int tid = threadIdx.y * RTX + threadIdx.x;
+        if (tid == 0) {
+            const int py = yb / ts, px = xb / ts;
+            const float2 f = __ldg(fl + (size_t)py * nx + px);
+            s.f = f;
+            s.S = tile_S(fl, py, px, ny, nx, p);
+            int sx[2], sy[2];
+            float wx[2][3], wy[2][3];
+            parity_weights(f.x, sx, wx);
+            parity_weights(f.y, sy, wy);
+            const int itx = (int)truncf(f.x), ity = (int)truncf(f.y);
+            int dj[4], di[2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dj[j] = ((itx + j) >> 1) + sx[(itx + j) & 1];      // window start of pixel j - (x0 >> 1)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) di[i] = ((ity + i) >> 1) + sy[(ity + i) & 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {
+                    const int k = m - (dj[j] - dj[0]);
+                    s.wx[j][m] = (k >= 0 && k < 3) ? wx[(itx + j) & 1][k] : 0.f;
+                }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int k = m - (di[i] - di[0]);
+                    s.wy[i][m] = (k >= 0 && k < 3) ? wy[(ity + i) & 1][k] : 0.f;
+                }
+            s.dx0 = dj[0], s.dy0 = di[0];
+            // every window of the block inside the guide image?  first window start >= 0, last window end <= n - 1
+            const int xl = min(xb + RTX * 4, W) - 4, yl = min(yb + RTY * 2, H) - 2;
+            s.fast = ((xb >> 1) + dj[0] >= 0) && ((xl >> 1) + dj[0] + 4 <= w - 1) && ((yb >> 1) + di[0] >= 0) &&
+                     ((yl >> 1) + di[0] + 3 <= h - 1);
+        }
         __syncthreads();
-        if (x >= W || y >= H) return;
-        ay = s_ay[threadIdx.y], ax = s_ax[threadIdx.x], S = s_S;
-    } else {
-        if (x >= W || y >= H) return;
-        const int py = y / ts, px = x / ts;
-        const float2 f = __ldg(fl + (size_t)py * nx + px);
-        S = tile_S(fl, py, px, ny, nx, p);
-        ay = dodgson_axis(y, f.y, h), ax = dodgson_axis(x, f.x, w);
     }
-    const unsigned plane = (unsigned)H * (unsigned)W, lplane = (unsigned)h * (unsigned)w, o = (unsigned)y * (unsigned)W + x;
-    float out = 0.f;   // any non-finite statistic ends as clamp(NaN) = 0 in the reference
-    const float rm0 = __ldg(ref_means + o);
-    if (ay.ok && ax.ok && isfinite(rm0)) {
-        float buf[3] = {0.f, 0.f, 0.f}, wacc;
-        if (ay.i[2] == ay.i[0] + 2 && ax.i[2] == ax.i[0] + 2) {
-            // interior: the 3x3 taps are contiguous -> one base pointer per (plane,row), immediate column offsets
-            const float *q0 = comp_lr + ((unsigned)ay.i[0] * (unsigned)w + (unsigned)ax.i[0]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float *qc = q0 + c * lplane;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const float *row = qc + i * w;
-                    const float r3 = fmaf(__ldg(row), ax.w[0], fmaf(__ldg(row + 1), ax.w[1], __ldg(row + 2) * ax.w[2]));
-                    buf[c] = fmaf(r3, ay.w[i], buf[c]);
-                }
+    if (x0 >= W || y0 >= H) return;
+    const unsigned plane = (unsigned)H * (unsigned)W, lplane = (unsigned)h * (unsigned)w;
+    if (!uniform || !s.fast) {
+#pragma unroll 1
+        for (int i = 0; i < 2; ++i)
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const int x = x0 + j, y = y0 + i;
+                if (x >= W || y >= H) continue;
+                const int py = y / ts, px = x / ts;
+                const float2 f = uniform ? s.f : __ldg(fl + (size_t)py * nx + px);
+                const float S = uniform ? s.S : tile_S(fl, py, px, ny, nx, p);
+                const Axis ay = dodgson_axis(y, f.y, h), ax = dodgson_axis(x, f.x, w);
+                R[(size_t)y * W + x] = robustness_pixel(comp_lr, ref_means, terms, H, W, x, y, ay, ax, S, p.t);
             }
-            wacc = (ay.w[0] + ay.w[1] + ay.w[2]) * (ax.w[0] + ax.w[1] + ax.w[2]);
-        } else {
-            wacc = 0.f;
+        return;
+    }
+    const float *win = comp_lr + (((y0 >> 1) + s.dy0) * w + ((x0 >> 1) + s.dx0));
+    const unsigned o = (unsigned)y0 * (unsigned)W + x0;
+    float d_sq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float rm0[2][4];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float *row = comp_lr + (unsigned)ay.i[i] * (unsigned)w;
+    for (int c = 0; c < 3; ++c) {
+        float col[2][5] = {{0.f, 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const float wgt = ay.w[i] * ax.w[j];
-                    const float *q = row + ax.i[j];
+        for (int m = 0; m < 4; ++m) {
+            const float *row = win + c * lplane + m * w;
+            const float w0 = s.wy[0][m], w1 = s.wy[1][m];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) buf[c] = fmaf(__ldg(q + c * lplane), wgt, buf[c]);
-                    wacc += wgt;
-                }
+            for (int n = 0; n < 5; ++n) {
+                const float v = __ldg(row + n);
+                col[0][n] = fmaf(v, w0, col[0][n]);
+                col[1][n] = fmaf(v, w1, col[1][n]);
             }
         }
-        const float inv_w = __fdividef(1.0f, wacc);
-        const float cm[3] = {buf[0] * inv_w, buf[1] * inv_w, buf[2] * inv_w};
-        out = robustness_value(cm, rm0, ref_means, ref_vars, o, plane, table, p, S);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float4 rm = __ldg(reinterpret_cast<const float4 *>(ref_means + o + c * plane + i * W));
+            const float4 dt = __ldg(reinterpret_cast<const float4 *>(terms + o + c * plane + i * W));
+            const float rmv[4] = {rm.x, rm.y, rm.z, rm.w}, dtv[4] = {dt.x, dt.y, dt.z, dt.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float cm = 0.f;
+#pragma unroll
+                for (int n = 0; n < 5; ++n) cm = fmaf(col[i][n], s.wx[j][n], cm);
+                d_sq[i][j] += shrunk_dist(rmv[j], cm, dtv[j]);
+                if (c == 0) rm0[i][j] = rmv[j];
+            }
+        }
     }
-    R[o] = out;
+    const float S = s.S;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float4 sg = __ldg(reinterpret_cast<const float4 *>(terms + o + 3 * plane + i * W));
+        const float sgv[4] = {sg.x, sg.y, sg.z, sg.w};
+        float out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = isfinite(rm0[i][j]) ? robustness_finish(d_sq[i][j], sgv[j], S, p.t) : 0.f;
+        *reinterpret_cast<float4 *>(R + o + i * W) = make_float4(out[0], out[1], out[2], out[3]);
+    }
 }
 
 __global__ void __launch_bounds__(RBX *RBY) local_min5_kernel(const float *__restrict__ R, int H, int W, float *__restrict__ r,
@@ -341,6 +456,58 @@ __global__ void __launch_bounds__(RBX *RBY) local_min5_kernel(const float *__res
     const size_t o = (size_t)y * W + x;
     r[o] = m;
     if (acc_rob) acc_rob[o] += (double)m;
+}
+
+// Vectorised variant (W % 4 == 0, 16-byte aligned rows): one thread = 4 consecutive pixels x LMR rows.  Each input row
+// is read once as three float4 (columns x-4 .. x+7, of which x-2 .. x+5 are used), reduced horizontally to the four
+// 5-wide minima, and a rolling window of the last five row results gives the vertical minimum: 3 LDG.128 per 4
+// output pixels and row instead of 25 shared-memory reads per pixel.  Minimum is order-independent, so the result is
+// bit-identical to local_min5_kernel.
+constexpr int LMR = 8;
+__global__ void __launch_bounds__(RBX *RBY) local_min5_vec4_kernel(const float *__restrict__ R, int H, int W, float *__restrict__ r,
+                                                                   double *__restrict__ acc_rob) {
+    const int x = (blockIdx.x * RBX + threadIdx.x) * 4, y0 = (blockIdx.y * RBY + threadIdx.y) * LMR;
+    if (x >= W || y0 >= H) return;
+    const bool inner = x >= 4 && x + 8 <= W;
+    float4 win[4];   // horizontal minima of the previous four rows
+#pragma unroll
+    for (int k = 0; k < LMR + 4; ++k) {
+        const int yy = min(max(y0 + k - 2, 0), H - 1);                     // clamp, robustness.py:680-681
+        const float *row = R + (size_t)yy * W;
+        float v[8];
+        if (inner) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(row + x - 4));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(row + x));
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(row + x + 4));
+            v[0] = a.z, v[1] = a.w, v[2] = b.x, v[3] = b.y, v[4] = b.z, v[5] = b.w, v[6] = c.x, v[7] = c.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(row + min(max(x + j - 2, 0), W - 1));
+        }
+        const float m12 = fminf(v[1], v[2]), m34 = fminf(v[3], v[4]), m56 = fminf(v[5], v[6]);
+        const float m1234 = fminf(m12, m34), m3456 = fminf(m34, m56);
+        float4 h;
+        h.x = fminf(v[0], m1234), h.y = fminf(m1234, v[5]), h.z = fminf(v[2], m3456), h.w = fminf(m3456, v[7]);
+        if (k >= 4) {
+            const int y = y0 + k - 4;
+            if (y < H) {
+                float4 m;
+                m.x = fminf(fminf(fminf(win[0].x, win[1].x), fminf(win[2].x, win[3].x)), h.x);
+                m.y = fminf(fminf(fminf(win[0].y, win[1].y), fminf(win[2].y, win[3].y)), h.y);
+                m.z = fminf(fminf(fminf(win[0].z, win[1].z), fminf(win[2].z, win[3].z)), h.z);
+                m.w = fminf(fminf(fminf(win[0].w, win[1].w), fminf(win[2].w, win[3].w)), h.w);
+                const size_t o = (size_t)y * W + x;
+                *reinterpret_cast<float4 *>(r + o) = m;
+                if (acc_rob) {
+                    double2 *a = reinterpret_cast<double2 *>(acc_rob + o);
+                    double2 a0 = a[0], a1 = a[1];
+                    a0.x += (double)m.x, a0.y += (double)m.y, a1.x += (double)m.z, a1.y += (double)m.w;
+                    a[0] = a0, a[1] = a1;
+                }
+            }
+        }
+        win[0] = win[1], win[1] = win[2], win[2] = win[3], win[3] = h;
+    }
 }
 
 }  // namespace hhsr
@@ -382,25 +549,45 @@ extern "C" int hhsr_noise_table(const double *std_curve, const double *diff_curv
     return launch_status("noise_table");
 }
 
-extern "C" int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_vars, int H,
-                               int W, const float *flow, int ny, int nx, int ts, const float *noise_table, int n_curve,
-                               double t, double s1, double s2, double Mt, float *R, hhsr_stream_t stream) {
-    HHSR_REQUIRE(comp_means_lr && ref_means && ref_vars && flow && noise_table && R, "null pointer");
+extern "C" int hhsr_robustness_ref_terms(const float *ref_means, const float *ref_vars, int H, int W,
+                                         const float *noise_table, int n_curve, float *terms, hhsr_stream_t stream) {
+    HHSR_REQUIRE(ref_means && ref_vars && noise_table && terms, "null pointer");
+    HHSR_REQUIRE(H > 0 && W > 0 && n_curve > 0, "non-positive size");
+    HHSR_REQUIRE((uintptr_t)noise_table % 8 == 0, "noise table must be 8-byte aligned");
+    const size_t plane = (size_t)H * W;
+    size_t blocks = (plane + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ref_noise_terms_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ref_means, ref_vars, plane,
+                                                                            reinterpret_cast<const float2 *>(noise_table),
+                                                                            n_curve, terms);
+    return launch_status("robustness_ref_terms");
+}
+
+extern "C" int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_terms, int H, int W,
+                               const float *flow, int ny, int nx, int ts, double t, double s1, double s2, double Mt,
+                               float *R, hhsr_stream_t stream) {
+    HHSR_REQUIRE(comp_means_lr && ref_means && ref_terms && flow && R, "null pointer");
     HHSR_REQUIRE(H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "frame sides must be even");
     HHSR_REQUIRE(ts > 0 && ny * ts >= H && nx * ts >= W, "flow grid does not cover the frame");
-    HHSR_REQUIRE(n_curve > 0, "empty noise curves");
-    HHSR_REQUIRE((uintptr_t)noise_table % 8 == 0, "noise table must be 8-byte aligned");
-    RobParams p{t, s1, s2, Mt, n_curve};
-    dim3 block(RBX, RBY), grid(ceil_div(W, RBX), ceil_div(H, RBY));
-    robustness_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(comp_means_lr, ref_means, ref_vars, H, W, flow, ny, nx, ts,
-                                                               reinterpret_cast<const float2 *>(noise_table), p, R);
+    HHSR_REQUIRE((uintptr_t)ref_means % 16 == 0 && (uintptr_t)ref_terms % 16 == 0 && (uintptr_t)R % 16 == 0,
+                 "ref_means / ref_terms / R must be 16-byte aligned");
+    const char *e = std::getenv("HHSR_ROBUSTNESS_GENERIC");     // A/B tests: force the per-pixel path
+    RobParams p{t, s1, s2, Mt, (e && e[0] == '1') ? 1 : 0};
+    dim3 block(RTX, RTY), grid(ceil_div(W, RTX * 4), ceil_div(H, RTY * 2));
+    robustness_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(comp_means_lr, ref_means, ref_terms, H, W, flow, ny, nx, ts, p, R);
     return launch_status("robustness");
 }
 
 extern "C" int hhsr_local_min5(const float *R, int H, int W, float *r, double *acc_rob, hhsr_stream_t stream) {
     HHSR_REQUIRE(R && r, "null pointer");
     HHSR_REQUIRE(H > 0 && W > 0, "non-positive size");
-    dim3 block(RBX, RBY), grid(ceil_div(W, RBX), ceil_div(H, RBY));
-    local_min5_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(R, H, W, r, acc_rob);
+    dim3 block(RBX, RBY);
+    if (W % 4 == 0 && (uintptr_t)R % 16 == 0 && (uintptr_t)r % 16 == 0 && (uintptr_t)acc_rob % 16 == 0) {
+        dim3 grid(ceil_div(W, RBX * 4), ceil_div(H, RBY * LMR));
+        local_min5_vec4_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(R, H, W, r, acc_rob);
+    } else {
+        dim3 grid(ceil_div(W, RBX), ceil_div(H, RBY));
+        local_min5_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(R, H, W, r, acc_rob);
+    }
     return launch_status("local_min5");
 }

@@ -58,6 +58,22 @@ def noise_table(noise_model):
     return table
 
 
+def ref_noise_terms(ref_local_means, ref_local_stds, table):
+    """Reference-side part of the noise model (robustness.py:504-533): [4, H, W] = (d_t^2 per channel, sum of
+    max(sigma_p^2, sigma_t^2)).  Depends on the reference frame only, so it is built once per burst and cached on the
+    `ref_local_means` tensor (the reference recomputes it for every comp frame)."""
+    key = (ref_local_stds.data_ptr(), table.data_ptr(), ref_local_means._version, ref_local_stds._version)
+    cached = getattr(ref_local_means, "_hhsr_noise_terms", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    _, H, W = ref_local_means.shape
+    terms = torch.empty((4, H, W), dtype=torch.float32, device=ref_local_means.device)
+    _lib.call("hhsr_robustness_ref_terms", _lib.ptr(ref_local_means), _lib.ptr(ref_local_stds), H, W, _lib.ptr(table),
+              table.shape[0], _lib.ptr(terms), _lib.stream())
+    ref_local_means._hhsr_noise_terms = (key, terms, ref_local_stds, table)   # keep the keyed tensors alive
+    return terms
+
+
 def local_min(R, acc_rob=None):
     """5x5 local minimum (Alg. 9, robustness.py:641-687); optionally fused with `acc_rob += r` (utils.add)."""
     R = _lib.as_device(R)
@@ -69,7 +85,8 @@ def local_min(R, acc_rob=None):
 def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pattern, white_balance, noise_model,
                        config, acc_rob=None, return_R=False):
     """Robustness map r [H, W] of comp frame J_n (Alg. 6, robustness.py:79-170).  Three launches: guide statistics
-    at half resolution, the fused per-pixel kernel (warp, distance, noise model, S, threshold), 5x5 minimum.
+    at half resolution, the fused per-pixel kernel (warp, distance, noise model, S, threshold), 5x5 minimum (plus,
+    for the first comp frame of a burst, the reference-side noise terms).
     `acc_rob` (float64 [H,W]), when given, is incremented by r in the last launch (super_resolution.py:159)."""
     comp_img = _lib.as_device(comp_img)
     H, W = comp_img.shape
@@ -83,8 +100,10 @@ def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pat
     flows = _lib.as_device(flows)
     comp_means, _ = compute_guide_stats(comp_img, cfa_pattern, white_balance, need_vars=False)
     R = torch.empty((H, W), dtype=torch.float32, device=comp_img.device)
-    _lib.call("hhsr_robustness", _lib.ptr(comp_means), _lib.ptr(ref_local_means), _lib.ptr(ref_local_stds), H, W,
-              _lib.ptr(flows), flows.shape[0], flows.shape[1], int(ts), _lib.ptr(table), table.shape[0],
+    ref_local_means = _lib.as_device(ref_local_means)
+    terms = ref_noise_terms(ref_local_means, _lib.as_device(ref_local_stds), table)
+    _lib.call("hhsr_robustness", _lib.ptr(comp_means), _lib.ptr(ref_local_means), _lib.ptr(terms), H, W,
+              _lib.ptr(flows), flows.shape[0], flows.shape[1], int(ts),
               float(tun.t), float(tun.s1), float(tun.s2), float(tun.Mt), _lib.ptr(R), _lib.stream())
     r = local_min(R, acc_rob)
     return (r, R) if return_R else r

@@ -100,12 +100,17 @@ int hhsr_upscale_warp_stats(const float *lr, int h, int w, const float *flow, in
 /* noise curves (float64, n_curve entries, as the reference uploads them, super_resolution.py:98-99) -> float32 table
  * [n_curve][2] = (sigma_t^2, d_t^2) read by hhsr_robustness; build once per burst. */
 int hhsr_noise_table(const double *std_curve, const double *diff_curve, int n_curve, float *table, hhsr_stream_t stream);
+/* reference-side part of the noise model (robustness.py:504-533), once per burst: terms [4][H][W] =
+ * (d_t^2 of channel 0, 1, 2 at the brightness level round(1000 * ref_mean), sum_c max(ref_var_c, sigma_t^2)).
+ * ref_means/ref_vars: [3][H][W] from hhsr_upscale_warp_stats; noise_table from hhsr_noise_table. */
+int hhsr_robustness_ref_terms(const float *ref_means, const float *ref_vars, int H, int W, const float *noise_table,
+                              int n_curve, float *terms, hhsr_stream_t stream);
 /* fused per-pixel robustness (robustness.py:421-639): warped Dodgson upsampling of the comp guide means,
  * |mean difference|, noise-model shrinkage, flow-irregularity factor S and threshold -> R [H][W].
- * ref_means/ref_vars: [3][H][W] from hhsr_upscale_warp_stats; noise_table from hhsr_noise_table. */
-int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_vars, int H, int W,
-                    const float *flow, int ny, int nx, int ts, const float *noise_table, int n_curve, double t,
-                    double s1, double s2, double Mt, float *R, hhsr_stream_t stream);
+ * ref_means: [3][H][W] from hhsr_upscale_warp_stats; ref_terms: [4][H][W] from hhsr_robustness_ref_terms. */
+int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_terms, int H, int W,
+                    const float *flow, int ny, int nx, int ts, double t, double s1, double s2, double Mt, float *R,
+                    hhsr_stream_t stream);
 /* 5x5 edge-replicated local minimum (robustness.py:641-687); when acc_rob != NULL also acc_rob += r
  * (utils.py:93-120, float64 accumulator). */
 int hhsr_local_min5(const float *R, int H, int W, float *r, double *acc_rob, hhsr_stream_t stream);
