@@ -301,31 +301,32 @@ struct RobTile {
     float2 f;
 };
 
-// parity classes e = 0, 1 of T = coordinate + trunc(flow): offset of the 3-tap window start relative to T >> 1 and the
-// (normalised) weights.  v = 0.5 e + 0.5 u - 0.5 with u = 0.5 + frac(flow) (see dodgson_axis).
-__device__ __forceinline__ void parity_weights(float fl, int (&start)[2], float (&wgt)[2][3]) {
-    const float u = 0.5f + (fl - truncf(fl));
+// Window of pixel (or row) k along one axis: T = coordinate + trunc(flow) has parity e = (it + k) & 1, the guide
+// position is (T >> 1) + v with v = 0.5 e + 0.5 u - 0.5, u = 0.5 + frac(flow) (see dodgson_axis); the 3 taps start at
+// (T >> 1) + rint(v) - 1.  Returns that start relative to (coordinate0 >> 1) (coordinate0 even) and the normalised
+// weights.  Ties of rint(): the extra tap has weight q(1.5) = 0 either way.
+__device__ __forceinline__ int axis_window(float fl, int k, float (&wgt)[3]) {
+    const float tf = truncf(fl);
+    const int it = (int)tf;
+    const float u = 0.5f + (fl - tf);
+    const float v = 0.5f * (float)((it + k) & 1) + 0.5f * u - 0.5f;
+    const int off = (int)rintf(v);
+    float sum = 0.f;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const float v = 0.5f * (float)e + 0.5f * u - 0.5f;
-        const int off = (int)rintf(v);          // ties: the extra tap has weight q(1.5) = 0 either way
-        start[e] = off - 1;
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            wgt[e][k] = dodgson_f((float)(off - 1 + k) - v);
-            sum += wgt[e][k];
-        }
-        const float inv = 1.0f / sum;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) wgt[e][k] *= inv;
+    for (int q = 0; q < 3; ++q) {
+        wgt[q] = dodgson_f((float)(off - 1 + q) - v);
+        sum += wgt[q];
     }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) wgt[q] *= inv;
+    return ((it + k) >> 1) + off - 1;
 }
 
-__global__ void __launch_bounds__(RTX *RTY) robustness_kernel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
-                                                              const float *__restrict__ terms, int H, int W,
-                                                              const float *__restrict__ flow, int ny, int nx, int ts,
-                                                              RobParams p, float *__restrict__ R) {
+__global__ void __launch_bounds__(RTX *RTY, 8) robustness_kernel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
+                                                                 const float *__restrict__ terms, int H, int W,
+                                                                 const float *__restrict__ flow, int ny, int nx, int ts,
+                                                                 RobParams p, float *__restrict__ R) {
     const float2 *fl = reinterpret_cast<const float2 *>(flow);
     const int h = H / 2, w = W / 2;
     const int xb = blockIdx.x * (RTX * 4), yb = blockIdx.y * (RTY * 2);
@@ -333,41 +334,38 @@ __global__ void __launch_bounds__(RTX *RTY) robustness_kernel(const float *__res
     __shared__ RobTile s;
     const bool uniform = (ts % 32) == 0 && (W % 4) == 0 && !p.force_generic;
     if (uniform) {
+        // prologue spread over the first warp: lanes 0-3 the x rows of the weight table, 4-5 the y rows, 6 the
+        // flow-irregularity factor, 7 the border test
         const int tid = threadIdx.y * RTX + threadIdx.x;
-        if (tid == 0) {
+        if (tid < 8) {
             const int py = yb / ts, px = xb / ts;
             const float2 f = __ldg(fl + (size_t)py * nx + px);
-            s.f = f;
-            s.S = tile_S(fl, py, px, ny, nx, p);
-            int sx[2], sy[2];
-            float wx[2][3], wy[2][3];
-            parity_weights(f.x, sx, wx);
-            parity_weights(f.y, sy, wy);
-            const int itx = (int)truncf(f.x), ity = (int)truncf(f.y);
-            int dj[4], di[2];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dj[j] = ((itx + j) >> 1) + sx[(itx + j) & 1];      // window start of pixel j - (x0 >> 1)
-#pragma unroll
-            for (int i = 0; i < 2; ++i) di[i] = ((ity + i) >> 1) + sy[(ity + i) & 1];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
+            float wgt[3], w0[3];
+            if (tid < 4) {
+                const int d = axis_window(f.x, tid, wgt) - axis_window(f.x, 0, w0);
 #pragma unroll
                 for (int m = 0; m < 5; ++m) {
-                    const int k = m - (dj[j] - dj[0]);
-                    s.wx[j][m] = (k >= 0 && k < 3) ? wx[(itx + j) & 1][k] : 0.f;
+                    const int k = m - d;
+                    s.wx[tid][m] = (k == 0) ? wgt[0] : (k == 1) ? wgt[1] : (k == 2) ? wgt[2] : 0.f;
                 }
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
+            } else if (tid < 6) {
+                const int d = axis_window(f.y, tid - 4, wgt) - axis_window(f.y, 0, w0);
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    const int k = m - (di[i] - di[0]);
-                    s.wy[i][m] = (k >= 0 && k < 3) ? wy[(ity + i) & 1][k] : 0.f;
+                    const int k = m - d;
+                    s.wy[tid - 4][m] = (k == 0) ? wgt[0] : (k == 1) ? wgt[1] : (k == 2) ? wgt[2] : 0.f;
                 }
-            s.dx0 = dj[0], s.dy0 = di[0];
-            // every window of the block inside the guide image?  first window start >= 0, last window end <= n - 1
-            const int xl = min(xb + RTX * 4, W) - 4, yl = min(yb + RTY * 2, H) - 2;
-            s.fast = ((xb >> 1) + dj[0] >= 0) && ((xl >> 1) + dj[0] + 4 <= w - 1) && ((yb >> 1) + di[0] >= 0) &&
-                     ((yl >> 1) + di[0] + 3 <= h - 1);
+            } else if (tid == 6) {
+                s.S = tile_S(fl, py, px, ny, nx, p);
+                s.f = f;
+            } else {
+                const int dj0 = axis_window(f.x, 0, wgt), di0 = axis_window(f.y, 0, w0);
+                s.dx0 = dj0, s.dy0 = di0;
+                // every window of the block inside the guide image?  first window start >= 0, last window end <= n - 1
+                const int xl = min(xb + RTX * 4, W) - 4, yl = min(yb + RTY * 2, H) - 2;
+                s.fast = ((xb >> 1) + dj0 >= 0) && ((xl >> 1) + dj0 + 4 <= w - 1) && ((yb >> 1) + di0 >= 0) &&
+                         ((yl >> 1) + di0 + 3 <= h - 1);
+            }
         }
         __syncthreads();
     }
@@ -391,7 +389,7 @@ __global__ void __launch_bounds__(RTX *RTY) robustness_kernel(const float *__res
     const float *win = comp_lr + (((y0 >> 1) + s.dy0) * w + ((x0 >> 1) + s.dx0));
     const unsigned o = (unsigned)y0 * (unsigned)W + x0;
     float d_sq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    float rm0[2][4];
+    unsigned finite = 0;   // bit i*4+j: reference mean of channel 0 is finite (not in the +inf band)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float col[2][5] = {{0.f, 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f, 0.f}};
@@ -417,7 +415,7 @@ __global__ void __launch_bounds__(RTX *RTY) robustness_kernel(const float *__res
 #pragma unroll
                 for (int n = 0; n < 5; ++n) cm = fmaf(col[i][n], s.wx[j][n], cm);
                 d_sq[i][j] += shrunk_dist(rmv[j], cm, dtv[j]);
-                if (c == 0) rm0[i][j] = rmv[j];
+                if (c == 0 && isfinite(rmv[j])) finite |= 1u << (i * 4 + j);
             }
         }
     }
@@ -428,7 +426,7 @@ __global__ void __launch_bounds__(RTX *RTY) robustness_kernel(const float *__res
         const float sgv[4] = {sg.x, sg.y, sg.z, sg.w};
         float out[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) out[j] = isfinite(rm0[i][j]) ? robustness_finish(d_sq[i][j], sgv[j], S, p.t) : 0.f;
+        for (int j = 0; j < 4; ++j) out[j] = ((finite >> (i * 4 + j)) & 1u) ? robustness_finish(d_sq[i][j], sgv[j], S, p.t) : 0.f;
         *reinterpret_cast<float4 *>(R + o + i * W) = make_float4(out[0], out[1], out[2], out[3]);
     }
 }

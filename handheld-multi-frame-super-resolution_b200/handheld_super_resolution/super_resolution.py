@@ -16,11 +16,98 @@ from .utils import add_many, divide, timer
 from .utils_image import compute_grey_images
 
 
-def _upload(frame, stream_ready=None):
-    """Host frame -> device (pinned staging handled by the caller for the async path)."""
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    """One persistent copy stream per device: a fresh torch stream per call would park the staging buffers in a
+    different per-stream allocator pool every time and force cudaMalloc in steady state."""
+    s = _COPY_STREAMS.get(device.index)
+    if s is None:
+        s = _COPY_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return s
+
+
+def _host_tensor(frame):
+    """numpy / torch host frame -> contiguous host tensor (float32, or uint16 sensor counts kept as they are)."""
     if isinstance(frame, torch.Tensor):
-        return frame.cuda(non_blocking=True) if not frame.is_cuda else frame
-    return torch.from_numpy(np.ascontiguousarray(frame, dtype=np.float32)).cuda(non_blocking=True)
+        t = frame
+    else:
+        a = np.ascontiguousarray(frame)
+        if a.dtype == np.uint16:
+            t = torch.from_numpy(a.view(np.int16)).view(torch.uint16)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    if t.dtype not in (torch.float32, torch.uint16):
+        t = t.to(torch.float32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class FrameFeeder:
+    """Frames of a burst -> normalised float32 CUDA tensors, streamed.
+
+    Host frames are copied on a persistent copy stream into a small ring of device staging buffers (allocated on the
+    compute stream, so the caching allocator serves them from the same pool every burst), one frame ahead of the
+    compute stream; uint16 frames (sensor counts) cross PCIe as 2 bytes per pixel and are normalised on the device
+    (utils_dng.RawNormalization, the reference's utils_dng.py:146-160).  CUDA float32 frames pass through."""
+    SLOTS = 3
+
+    def __init__(self, frames, ids, config, device):
+        self.frames, self.ids, self.config, self.device = frames, list(ids), config, device
+        self.compute = torch.cuda.current_stream(device)
+        self.copy = _copy_stream(device)
+        self.norm = None
+        self.ring, self.free_ev, self.ready = {}, {}, {}
+        self.next_k = 0
+
+    def _stage(self, k):
+        """Enqueue the H2D copy of the k-th frame of `ids` (no-op for device frames)."""
+        if k >= len(self.ids) or k in self.ready:
+            return
+        frame = self.frames[self.ids[k]]
+        if isinstance(frame, torch.Tensor) and frame.is_cuda:
+            self.ready[k] = (frame, None)
+            return
+        host = _host_tensor(frame)
+        key = (host.dtype, k % self.SLOTS)
+        if key not in self.ring:
+            self.ring[key] = torch.empty(host.shape, dtype=host.dtype, device=self.device)   # compute-stream pool
+            ev = torch.cuda.Event()
+            ev.record(self.compute)        # the block may still be in use by earlier work of the compute stream
+            self.free_ev[key] = ev
+        buf = self.ring[key]
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(self.free_ev[key])       # previous user of this slot is done
+            buf.copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy)
+        self.ready[k] = (buf, ev, key)
+
+    def get(self, k):
+        """k-th frame as float32 on the compute stream; prefetches frame k + 1.  Call release(k) after its last use."""
+        self._stage(k)
+        self._stage(k + 1)
+        item = self.ready[k]
+        if item[1] is None:
+            return self._normalised(item[0])
+        buf, ev, key = item
+        self.compute.wait_event(ev)
+        return self._normalised(buf)
+
+    def _normalised(self, t):
+        if t.dtype == torch.uint16:
+            if self.norm is None:
+                from .utils_dng import RawNormalization
+                self.norm = RawNormalization.from_config(self.config)
+            return self.norm.apply(t)
+        return t if t.dtype == torch.float32 else t.to(torch.float32)
+
+    def release(self, k):
+        item = self.ready.pop(k, None)
+        if item is not None and item[1] is not None:
+            ev = torch.cuda.Event()
+            ev.record(self.compute)
+            self.free_ev[item[2]] = ev
 
 
 def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
@@ -50,7 +137,11 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
     dev = torch.device("cuda", torch.cuda.current_device())
     t1 = time.perf_counter()
 
-    cuda_ref_img = _upload(ref_img)
+    ref_feed = FrameFeeder([ref_img], [0], config, dev)
+    cuda_ref_img = ref_feed.get(0)
+    if any(cuda_ref_img is b for b in ref_feed.ring.values()):
+        cuda_ref_img = cuda_ref_img.clone()      # the reference frame outlives its staging slot
+    ref_feed.release(0)
     cfa_pattern = config.exif.cfa_pattern
     white_balance = config.exif.white_balance
     from .robustness import noise_table
@@ -69,29 +160,11 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
     accumulated_r = torch.zeros((H, W), dtype=torch.float64, device=dev) if accumulate_r else None
 
     n_images = len(comp_imgs)
-    ids = range(n_images) if frame_ids is None else frame_ids
-    copy_stream = torch.cuda.Stream()
-    compute_stream = torch.cuda.current_stream()
-    pending = {}
-
-    def prefetch(i):   # H2D of frame i on the copy stream, overlapped with compute on the previous frame
-        if i is None or i in pending:
-            return
-        with torch.cuda.stream(copy_stream):
-            t = _upload(comp_imgs[i])
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        pending[i] = (t, ev)
-
-    ids = list(ids)
+    ids = list(range(n_images) if frame_ids is None else frame_ids)
+    feed = FrameFeeder(comp_imgs, ids, config, dev)
     r_maps = []
-    if ids:
-        prefetch(ids[0])
     for k, im_id in enumerate(ids):
-        prefetch(ids[k + 1] if k + 1 < len(ids) else None)
-        cuda_img, ev = pending.pop(im_id)
-        compute_stream.wait_event(ev)
-        cuda_img.record_stream(compute_stream)
+        cuda_img = feed.get(k)          # H2D of frame k+1 overlaps the work on frame k
         cuda_im_grey = compute_grey_images(cuda_img, grey_method)
         flow = align_(ref_pyramid, tyled_pyr, ref_tiled_fft, ref_gradx, ref_grady, ref_hessian, cuda_im_grey, config)
         if debug_mode:
@@ -102,6 +175,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
             r_maps.append(r)      # accumulated_r += r (super_resolution.py:159), summed in frame order after the loop
         covs = estimate_kernels_(cuda_img, config)
         merge_(cuda_img, flow, covs, r, num, den, cfa_pattern, config)
+        feed.release(k)
         if debug_mode:
             debug_dict["robustness"].append(r.cpu().numpy())
 
@@ -153,8 +227,24 @@ def process(burst_path, config):
     from .config import Config
     from .noise_model import run_fast_MC
     data = load_burst(burst_path)
-    burst = np.asarray(data["burst"], dtype=np.float32)
-    ref_raw, raw_comp = burst[0], burst[1:]
+    burst = np.asarray(data["burst"])
+    cfa = np.asarray(data.get("cfa_pattern", [[0, 1], [1, 2]])).tolist()
+    wb = np.asarray(data.get("white_balance", [1.0, 1.0, 1.0, 0.0]), dtype=np.float64).tolist()
+    raw_levels = None
+    if np.issubdtype(burst.dtype, np.integer):
+        # sensor counts: normalised like utils_dng.py:146-160 — on the device, frame by frame, inside main();
+        # only the reference frame is also normalised here, for the SNR estimate below
+        from .utils_dng import RawNormalization
+        if "black_levels" not in data or "white_level" not in data:
+            raise ValueError("integer burst: the archive must provide black_levels and white_level")
+        raw_levels = (np.asarray(data["black_levels"]).reshape(-1).tolist(), int(data["white_level"]))
+        burst = burst.astype(np.uint16)
+        ref_raw = RawNormalization(cfa, raw_levels[0], raw_levels[1], wb).apply_numpy(burst[0])
+        ref_in, raw_comp = burst[0], burst[1:]
+    else:
+        burst = burst.astype(np.float32)
+        ref_raw = ref_in = burst[0]
+        raw_comp = burst[1:]
     if config.noise_model.get("alpha", None) is None:
         if "alpha" not in data:
             raise ValueError("noise model: alpha/beta neither in the config nor in the burst archive")
@@ -168,16 +258,15 @@ def process(burst_path, config):
     SNR = brightness / std_curve[round(1000 * brightness)]
     update_snr_config(config, SNR)
     sanitize_config(config, ref_raw.shape)
-    config.exif = Config.wrap({
-        "cfa_pattern": np.asarray(data.get("cfa_pattern", [[0, 1], [1, 2]])).tolist(),
-        "iso": int(data.get("iso", 100)),
-        "white_balance": np.asarray(data.get("white_balance", [1.0, 1.0, 1.0, 0.0]), dtype=np.float64).tolist()})
+    config.exif = Config.wrap({"cfa_pattern": cfa, "iso": int(data.get("iso", 100)), "white_balance": wb})
+    if raw_levels is not None:
+        config.exif.black_levels, config.exif.white_level = raw_levels
     config.noise_model.update({"std_curve": std_curve.tolist(), "diff_curve": diff_curve.tolist()})
     ard = config.accumulated_robustness_denoiser
     ard.enabled = bool(any(x.enabled for x in (ard.median, ard.gauss, ard.merge)))
     if ard.median.enabled or ard.gauss.enabled:
         raise NotImplementedError("post-merge frame-count denoisers are out of scope (SURVEY section 2, row 17)")
-    out, debug_dict = main(ref_raw, raw_comp, config)
+    out, debug_dict = main(ref_in, raw_comp, config)
     output_image = out.cpu().numpy()
     if "accumulated robustness" in debug_dict:
         debug_dict["accumulated robustness"] = debug_dict["accumulated robustness"].cpu().numpy()

@@ -115,6 +115,12 @@ int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const fl
  * (utils.py:93-120, float64 accumulator). */
 int hhsr_local_min5(const float *R, int H, int W, float *r, double *acc_rob, hhsr_stream_t stream);
 
+/* ---- RAW input (utils_dng.py:146-160): sensor counts uint16 [H][W] -> normalised float32
+ * out = (float(raw) - black4[p]) / den4[p] * gain4[p], p = (row & 1) * 2 + (col & 1) the CFA position, every
+ * operation rounded to float32 like the reference's NumPy code (den = white - black, gain = wb[c] / wb[1]). */
+int hhsr_normalize_raw_u16(const unsigned short *raw, int H, int W, const float *black4, const float *den4,
+                           const float *gain4, float *out, hhsr_stream_t stream);
+
 /* ---- merge, Alg. 4 (merge.py:236-434): accumulate one aligned comp frame into num/den [Hs][Ws][3].
  * iso: 0 steerable kernel, 1 isotropic. */
 int hhsr_merge_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,

@@ -34,6 +34,23 @@ def fma32(a, b, c):
     return (np.asarray(a, F64) * np.asarray(b, F64) + np.asarray(c, F64)).astype(F32)
 
 
+def normalize_raw(raw, cfa, black_levels, white_level, white_balance):
+    """utils_dng.py:146-160, literally: integer sensor counts [..., H, W] -> float32, per CFA position
+    (x - black[c]) / (white - black[c]) then *= wb[c] / wb[1], with the reference's Python-scalar operands (ints for
+    the levels, a float for the gain) so NumPy rounds them exactly as it does there."""
+    x = np.asarray(raw).astype(F32)
+    black = [int(b) for b in black_levels]
+    white = int(white_level)
+    wb = [float(w) for w in white_balance]
+    for i in range(2):
+        for j in range(2):
+            channel = int(cfa[i][j])
+            k = wb[channel] / wb[1]
+            x[..., i::2, j::2] = (x[..., i::2, j::2] - black[channel]) / (white - black[channel])
+            x[..., i::2, j::2] *= k
+    return x
+
+
 # --------------------------------------------------------------------------------------------------------------
 # Grey image (Alg. 3) — utils_image.py:82-100
 # --------------------------------------------------------------------------------------------------------------

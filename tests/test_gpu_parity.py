@@ -398,6 +398,44 @@ def test_local_min_against_torch(shape):
     assert torch.equal(acc, 2.0 + want.double())
 
 
+@pytest.mark.parametrize("shape", [(64, 96), (70, 100), (3000, 4000)])
+def test_raw_normalisation_kernel_bit_exact(shape):
+    """hhsr_normalize_raw_u16 (vectorised and scalar variants) against the reference's NumPy loop (oracle)."""
+    import hhsr_oracle as O
+    from handheld_super_resolution.utils_dng import RawNormalization
+    rng = np.random.default_rng(shape[0])
+    raw = rng.integers(0, 16384, size=shape, dtype=np.uint16)
+    cfa, black, white, wb = [[1, 2], [0, 1]], [1024, 1023, 1025, 1023], 16383, [2.1, 1.0, 1.63, 0.0]
+    want = O.normalize_raw(raw, cfa, black, white, wb)
+    dev_raw = torch.from_numpy(raw.view(np.int16)).view(torch.uint16).cuda()
+    got = host(RawNormalization(cfa, black, white, wb).apply(dev_raw))
+    assert np.array_equal(got, want)
+
+
+def test_main_uint16_burst_equals_float_burst():
+    """main() fed with sensor counts (uint16 host frames, normalised on the device) must equal main() fed with the
+    host-normalised float32 burst bit for bit; also exercises the streamed H2D ring with more frames than slots."""
+    import hhsr_oracle as O
+    from handheld_super_resolution import main
+    from handheld_super_resolution.synthetic import synth_burst
+    burst, _ = synth_burst(6, 96, 128, seed=9, max_shift=2.0, quantize_bits=12)
+    black, white = [256, 256, 256, 256], 4095
+    counts = np.round(burst * (white - 256) + 256).astype(np.uint16)
+    kw = dict(scale=2, tile_size=16, tile_sizes=[16, 16, 8], factors=[1, 2, 2], metrics=["L2", "L2", "L2"],
+              search_radii=[2, 4, 4])
+    cfg = attr_cfg(**kw)
+    cfg.exif.white_balance = [1.0, 1.0, 1.0, 0.0]
+    cfg.exif.black_levels, cfg.exif.white_level = black, white
+    fburst = O.normalize_raw(counts, CFA, black, white, cfg.exif.white_balance)
+    out_f, _ = main(fburst[0], fburst[1:], cfg)
+    out_u, _ = main(counts[0], counts[1:], cfg)
+    pinned = torch.from_numpy(fburst).pin_memory()
+    out_p, _ = main(pinned[0], pinned[1:], cfg)
+    out_d, _ = main(pinned[0].cuda(), pinned[1:].cuda(), cfg)
+    for o in (out_u, out_p, out_d):
+        assert torch.equal(torch.nan_to_num(out_f), torch.nan_to_num(o))
+
+
 def test_divide_and_add():
     from handheld_super_resolution.utils import add, divide
     g = torch.Generator(device="cuda").manual_seed(0)

@@ -152,3 +152,18 @@ def test_frame_sharding():
         sizes = [len(p) for p in parts]
         assert max(sizes) - min(sizes) <= 1
     assert [len(shard_frames(19, r, 8)) for r in range(8)] == [3, 3, 3, 2, 2, 2, 2, 2]
+
+
+def test_raw_normalisation_host_matches_reference_loop():
+    """RawNormalization.apply_numpy (the constants the device kernel uses, rounded to float32 up front) against the
+    literal reference loop with Python-scalar operands (oracle.normalize_raw, utils_dng.py:146-160): bit-identical."""
+    import hhsr_oracle as O
+    from handheld_super_resolution.utils_dng import RawNormalization
+    rng = np.random.default_rng(0)
+    raw = rng.integers(0, 16384, size=(3, 64, 96), dtype=np.uint16)
+    for cfa, black, white, wb in [([[0, 1], [1, 2]], [1024, 1023, 1025, 1023], 16383, [2.1, 1.0, 1.63, 0.0]),
+                                  ([[1, 2], [0, 1]], [64, 64, 64, 64], 1023, [1.91, 1.07, 1.4, 1.07]),
+                                  ([[2, 1], [1, 0]], [0, 0, 0, 0], 4095, [1.0, 1.0, 1.0, 1.0])]:
+        want = O.normalize_raw(raw, cfa, black, white, wb)
+        got = RawNormalization(cfa, black, white, wb).apply_numpy(raw)
+        assert got.dtype == np.float32 and np.array_equal(got, want)

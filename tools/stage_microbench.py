@@ -37,7 +37,8 @@ def main():
     rm, rs = RB.init_robustness(ref, cfa, wb, cfg)
     grey = compute_grey_images(img, "FFT")
     flow = AL.align(*refal, grey, cfg)
-    r = RB.compute_robustness(img, rm, rs, flow, cfa, wb, (std, diff), cfg)
+    table = RB.noise_table((std, diff))      # built once per burst, like main()
+    r = RB.compute_robustness(img, rm, rs, flow, cfa, wb, table, cfg)
     covs = estimate_kernels(img, cfg)
     hs, ws = round(scale * a.H), round(scale * a.W)
     num = torch.zeros((hs, ws, 3), device="cuda")
@@ -59,7 +60,7 @@ def main():
         "grey_fft": lambda: compute_grey_images(img, "FFT"),
         "pyramid": lambda: AL.build_gaussian_pyramid(grey, cfg.block_matching.tuning.factors),
         "align": lambda: AL.align(*refal, grey, cfg),
-        "robustness": lambda: RB.compute_robustness(img, rm, rs, flow, cfa, wb, (std, diff), cfg),
+        "robustness": lambda: RB.compute_robustness(img, rm, rs, flow, cfa, wb, table, cfg),
         "estimate_kernels": lambda: estimate_kernels(img, cfg),
         "merge": lambda: MG.merge(img, flow, covs, r, num, den, cfa, cfg),
         "merge_ref": lambda: MG.merge_ref(ref, covs, num, den, cfa, cfg),
