@@ -26,6 +26,15 @@
 #ifndef HHSR_MERGE_POW2_MINBLOCKS
 #define HHSR_MERGE_POW2_MINBLOCKS 4
 #endif
+#ifndef HHSR_MERGE_RMW_END
+#define HHSR_MERGE_RMW_END 0     // 1: read-modify-write the whole 12-float slice after the fourth pixel
+#endif
+#ifndef HHSR_MERGE_PREFETCH
+#define HHSR_MERGE_PREFETCH 1
+#endif
+#ifndef HHSR_MERGE_BLOCK_Y
+#define HHSR_MERGE_BLOCK_Y 8
+#endif
 #ifndef HHSR_MERGE_REUSE_QUADS
 #define HHSR_MERGE_REUSE_QUADS 0
 #endif
@@ -84,6 +93,14 @@ static MergeGeom make_geom(int H, int W, int nx, int ts, int Hs, int Ws, const i
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// acc + r * x with the product rounded separately and flush-to-zero addition: the arithmetic of the L2 reduction the
+// fast path uses (see rmw4)
+__device__ __forceinline__ float add_ftz(float acc, float r, float x) {
+    float y;
+    asm("add.ftz.f32 %0, %1, %2;" : "=f"(y) : "f"(acc), "f"(r * x));
     return y;
 }
 
@@ -148,7 +165,7 @@ __device__ __forceinline__ void merge_taps(const float *__restrict__ pc, int H, 
 }
 
 // Fold the four parity partials into the three colour channels (unscaled: every kernel applies the robustness as
-// acc = fmaf(r, sum, acc), one rounding, so single-frame, batched and fast-path launches agree bit for bit).
+// acc = add_ftz(acc, r * sum), so single-frame, batched and fast-path launches agree bit for bit).
 // Bayer patterns take 7 selects; anything else the generic 12.
 __device__ __forceinline__ void resolve_channels(const CfaInfo &cf, int ci, int cj, const float (&v)[2][2], float (&out)[3]) {
     float ch[3];
@@ -302,10 +319,10 @@ __device__ __forceinline__ void accumulate_thread(const MergeFrame &f, const Mer
         for (int q = 0; q < 3; ++q) {
             float4 a = *reinterpret_cast<const float4 *>(num + base + 4 * q);
             float4 c = *reinterpret_cast<const float4 *>(den + base + 4 * q);
-            a.x = fmaf(rr[(4 * q) / 3], nf[4 * q], a.x), a.y = fmaf(rr[(4 * q + 1) / 3], nf[4 * q + 1], a.y);
-            a.z = fmaf(rr[(4 * q + 2) / 3], nf[4 * q + 2], a.z), a.w = fmaf(rr[(4 * q + 3) / 3], nf[4 * q + 3], a.w);
-            c.x = fmaf(rr[(4 * q) / 3], df[4 * q], c.x), c.y = fmaf(rr[(4 * q + 1) / 3], df[4 * q + 1], c.y);
-            c.z = fmaf(rr[(4 * q + 2) / 3], df[4 * q + 2], c.z), c.w = fmaf(rr[(4 * q + 3) / 3], df[4 * q + 3], c.w);
+            a.x = add_ftz(a.x, rr[(4 * q) / 3], nf[4 * q]), a.y = add_ftz(a.y, rr[(4 * q + 1) / 3], nf[4 * q + 1]);
+            a.z = add_ftz(a.z, rr[(4 * q + 2) / 3], nf[4 * q + 2]), a.w = add_ftz(a.w, rr[(4 * q + 3) / 3], nf[4 * q + 3]);
+            c.x = add_ftz(c.x, rr[(4 * q) / 3], df[4 * q]), c.y = add_ftz(c.y, rr[(4 * q + 1) / 3], df[4 * q + 1]);
+            c.z = add_ftz(c.z, rr[(4 * q + 2) / 3], df[4 * q + 2]), c.w = add_ftz(c.w, rr[(4 * q + 3) / 3], df[4 * q + 3]);
             *reinterpret_cast<float4 *>(num + base + 4 * q) = a;
             *reinterpret_cast<float4 *>(den + base + 4 * q) = c;
         }
@@ -315,8 +332,8 @@ __device__ __forceinline__ void accumulate_thread(const MergeFrame &f, const Mer
             if (j0 + p < g.Ws)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    num[base + p * 3 + c] = fmaf(rr[p], n[p][c], num[base + p * 3 + c]);
-                    den[base + p * 3 + c] = fmaf(rr[p], d[p][c], den[base + p * 3 + c]);
+                    num[base + p * 3 + c] = add_ftz(num[base + p * 3 + c], rr[p], n[p][c]);
+                    den[base + p * 3 + c] = add_ftz(den[base + p * 3 + c], rr[p], d[p][c]);
                 }
     }
 }
@@ -359,12 +376,14 @@ __device__ __noinline__ void accumulate_thread_border(const MergeFrame *f, const
     accumulate_thread<ISO, 4>(*f, *g, num, den, hr_i, j0);
 }
 
-// p[0..3] = fmaf(r_k, x_k, p[0..3])
+// p[0..3] += r_k * x_k as ONE fire-and-forget 16-byte reduction performed by the L2 (REDG.E.ADD.F32x4): the SM never
+// loads the accumulators, so their HBM/L2 latency is off the warps' critical path.  Each address receives exactly one
+// reduction per launch (deterministic).  Like every f32 atomic the L2 adder flushes subnormals (add.ftz); the generic
+// kernels use add_ftz() below so that all merge kernels still agree bit for bit.
 __device__ __forceinline__ void rmw4(float *__restrict__ p, float r0, float a, float r1, float b, float r2, float c, float r3,
                                      float d) {
-    float4 v = *reinterpret_cast<const float4 *>(p);
-    v.x = fmaf(r0, a, v.x), v.y = fmaf(r1, b, v.y), v.z = fmaf(r2, c, v.z), v.w = fmaf(r3, d, v.w);
-    *reinterpret_cast<float4 *>(p) = v;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r0 * a), "f"(r1 * b), "f"(r2 * c), "f"(r3 * d)
+                 : "memory");
 }
 
 // Interior 3x3 taps addressed by a 32-bit element offset `o` of the centre tap (one IMAD.WIDE per row, immediates
@@ -401,7 +420,7 @@ __device__ __forceinline__ void resolve_rggb(bool sy, bool sx, const float (&v)[
 }
 
 template <bool ISO, int K>
-__global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_kernel(const __grid_constant__ MergeFrame f,
+__global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_kernel(const __grid_constant__ MergeFrame f,
                                                                                      const __grid_constant__ MergeGeom g,
                                                                                      float *__restrict__ num,
                                                                                      float *__restrict__ den) {
@@ -411,7 +430,7 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (hr_i >= g.Hs || j0 >= g.Ws) return;
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
-    if ((threadIdx.x & 1) == 0) {
+    if (HHSR_MERGE_PREFETCH && (threadIdx.x & 1) == 0) {
         prefetch_l2(num + base);
         prefetch_l2(den + base);
         prefetch_l2(num + base + 23);
@@ -480,8 +499,9 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow
         resolve_rggb(sy, sx, a, acc);
 #pragma unroll
         for (int c = 0; c < 3; ++c) n[3 * p + c] = val[c], d[3 * p + c] = acc[c];
-        if (p >= 1) {   // float4 number p-1 of the 12-float slice is complete
-            const int q = p - 1;
+        if (HHSR_MERGE_RMW_END ? (p == 3) : (p >= 1))
+#pragma unroll
+        for (int q = (HHSR_MERGE_RMW_END ? 0 : p - 1); q <= p - 1; ++q) {   // float4 number q of the 12-float slice is complete
             rmw4(num + base + 4 * q, rr[(4 * q) / 3], n[4 * q], rr[(4 * q + 1) / 3], n[4 * q + 1], rr[(4 * q + 2) / 3],
                  n[4 * q + 2], rr[(4 * q + 3) / 3], n[4 * q + 3]);
             rmw4(den + base + 4 * q, rr[(4 * q) / 3], d[4 * q], rr[(4 * q + 1) / 3], d[4 * q + 1], rr[(4 * q + 2) / 3],
@@ -532,8 +552,8 @@ __global__ void __launch_bounds__(256, 2) accumulate_batch_kernel(MergeBatch b, 
             const float rl = merge_hr_pixel<ISO>(b.f[k], g, j0 + p, rc, cq, val, acc);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                n[p * 3 + c] = fmaf(rl, val[c], n[p * 3 + c]);
-                d[p * 3 + c] = fmaf(rl, acc[c], d[p * 3 + c]);
+                n[p * 3 + c] = add_ftz(n[p * 3 + c], rl, val[c]);
+                d[p * 3 + c] = add_ftz(d[p * 3 + c], rl, acc[c]);
             }
         }
     }
@@ -724,7 +744,8 @@ static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num
     dim3 block(32, 8);
     const int k = b.K == 1 ? pow2_fast_shift(g) : -1;
     if (k >= 0) {
-        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8));
+        block = dim3(32, HHSR_MERGE_BLOCK_Y);
+        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, HHSR_MERGE_BLOCK_Y));
         if (k == 0) launch_pow2<0>(b.f[0], g, num, den, iso, grid, block, st);
         if (k == 1) launch_pow2<1>(b.f[0], g, num, den, iso, grid, block, st);
         if (k == 2) launch_pow2<2>(b.f[0], g, num, den, iso, grid, block, st);

@@ -17,6 +17,15 @@ from .utils_image import compute_grey_images
 
 
 _COPY_STREAMS = {}
+PHASE_EVENTS = None     # set to a list to collect (phase name, CUDA event) marks of main() (tools/phase_breakdown.py)
+
+
+def _mark(name):
+    if PHASE_EVENTS is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        PHASE_EVENTS.append((name, ev))
+
 
 
 def _copy_stream(device):
@@ -137,6 +146,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
     dev = torch.device("cuda", torch.cuda.current_device())
     t1 = time.perf_counter()
 
+    _mark("start")
     ref_feed = FrameFeeder([ref_img], [0], config, dev)
     cuda_ref_img = ref_feed.get(0)
     if any(cuda_ref_img is b for b in ref_feed.ring.values()):
@@ -159,6 +169,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
     den = torch.zeros((*output_size, 3), dtype=torch.float32, device=dev)
     accumulated_r = torch.zeros((H, W), dtype=torch.float64, device=dev) if accumulate_r else None
 
+    _mark("ref_side")
     n_images = len(comp_imgs)
     ids = list(range(n_images) if frame_ids is None else frame_ids)
     feed = FrameFeeder(comp_imgs, ids, config, dev)
@@ -186,16 +197,20 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
     # the one reduction point of the pipeline (frame-sharded runs): reduce_fn sums the accumulators across ranks and
     # may hand back the slice of output rows this rank has to normalise plus a callable that re-assembles the image
     rows, gather_fn = None, None
+    _mark("frames")
     if reduce_fn is not None:
         res = reduce_fn(num, den, accumulated_r)
         if res is not None:
             rows, gather_fn = res
+    _mark("reduce")
 
     covs = estimate_kernels_(cuda_ref_img, config)
     use_acc = accumulated_r if config.accumulated_robustness_denoiser.enabled else None
     merge_ref_(cuda_ref_img, covs, num, den, cfa_pattern, config, use_acc, fuse_divide=True, rows=rows)   # + utils.divide, :191
+    _mark("merge_ref")
     if gather_fn is not None:
         gather_fn(num)
+    _mark("gather")
 
     if config.verbose >= 1:
         torch.cuda.synchronize()
