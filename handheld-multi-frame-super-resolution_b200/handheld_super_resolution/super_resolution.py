@@ -37,6 +37,18 @@ def _copy_stream(device):
     return s
 
 
+_ALIGN_STREAMS = {}
+
+
+def _align_stream(device):
+    """Persistent high-priority side stream on which the alignment chain of frame k+1 (grey image, pyramid, block
+    matching, ICA: many small latency-bound launches) runs while the main stream weights and merges frame k."""
+    s = _ALIGN_STREAMS.get(device.index)
+    if s is None:
+        s = _ALIGN_STREAMS[device.index] = torch.cuda.Stream(device=device, priority=-1)
+    return s
+
+
 def _host_tensor(frame):
     """numpy / torch host frame -> contiguous host tensor (float32, or uint16 sensor counts kept as they are)."""
     if isinstance(frame, torch.Tensor):
@@ -174,10 +186,34 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
     ids = list(range(n_images) if frame_ids is None else frame_ids)
     feed = FrameFeeder(comp_imgs, ids, config, dev)
     r_maps = []
-    for k, im_id in enumerate(ids):
+    main_stream = torch.cuda.current_stream(dev)
+    two_streams = os.environ.get("HHSR_SINGLE_STREAM", "0") != "1" and not verbose_2
+    align_stream = _align_stream(dev) if two_streams else main_stream
+
+    def start_alignment(k):
+        """Frame k: H2D wait (+ uint16 normalisation) on the main stream, then grey image and alignment on the
+        alignment stream.  Returns (frame, flow, event marking the flow ready)."""
         cuda_img = feed.get(k)          # H2D of frame k+1 overlaps the work on frame k
-        cuda_im_grey = compute_grey_images(cuda_img, grey_method)
-        flow = align_(ref_pyramid, tyled_pyr, ref_tiled_fft, ref_gradx, ref_grady, ref_hessian, cuda_im_grey, config)
+        if not two_streams:
+            grey = compute_grey_images(cuda_img, grey_method)
+            return cuda_img, align_(ref_pyramid, tyled_pyr, ref_tiled_fft, ref_gradx, ref_grady, ref_hessian, grey, config), None
+        ready = torch.cuda.Event()
+        ready.record(main_stream)       # frame (and, the first time, the reference-side products) are ready
+        with torch.cuda.stream(align_stream):
+            align_stream.wait_event(ready)
+            grey = compute_grey_images(cuda_img, grey_method)
+            flow = align_(ref_pyramid, tyled_pyr, ref_tiled_fft, ref_gradx, ref_grady, ref_hessian, grey, config)
+            done = torch.cuda.Event()
+            done.record(align_stream)
+        return cuda_img, flow, done
+
+    nxt = start_alignment(0) if ids else None
+    for k, im_id in enumerate(ids):
+        cuda_img, flow, done = nxt
+        nxt = start_alignment(k + 1) if k + 1 < len(ids) else None     # overlaps the rest of this iteration
+        if done is not None:
+            main_stream.wait_event(done)
+            flow.record_stream(main_stream)
         if debug_mode:
             debug_dict["flow"].append(flow.cpu().numpy())
         r = compute_robustness_(cuda_img, ref_local_means, ref_local_stds, flow, cfa_pattern, white_balance,
