@@ -17,13 +17,24 @@ constexpr int KBX = 32, KBY = 8;
 
 struct KernelParams {
     double alpha, beta, k_detail, k_denoise, D_th, D_tr, k_stretch, k_shrink;
+    double inv_D_tr, inv_k_shrink;   // host-side reciprocals (one float64 division per launch instead of per thread)
     int law;  // 0 hard threshold, 1 linear
 };
+
+// float64 square root to < 2 ulp from a float32 rsqrt seed and two Newton steps (10 instructions against ~30 for the
+// IEEE sqrt sequence); every use below rounds the result to float32, which absorbs the difference.
+__device__ __forceinline__ double sqrt_fast(double v) {
+    if (!(v > 1e-30 && v < 1e30)) return sqrt(v);      // zero, tiny, huge, negative, NaN: the IEEE sequence
+    double r = (double)rsqrtf((float)v);
+    r = fma(0.5 * r, fma(-v * r, r, 1.0), r);          // rsqrt to ~46 bits
+    const double s = v * r;
+    return fma(fma(-s, s, v), 0.5 * r, s);
+}
 
 __device__ __forceinline__ float gat_px(float x, double alpha, double c0, double two_over_alpha) {
     double v = alpha * (double)x + c0;           // alpha*I + 3/8*alpha^2 + beta   (utils_image.py:165)
     v = (v > 0.0) ? v : 0.0;
-    return (float)(two_over_alpha * sqrt(v));
+    return (float)(two_over_alpha * sqrt_fast(v));
 }
 
 __global__ void __launch_bounds__(KBX *KBY) estimate_kernels_kernel(const float *__restrict__ raw, int H, int W, int h,
@@ -43,7 +54,7 @@ __global__ void __launch_bounds__(KBX *KBY) estimate_kernels_kernel(const float 
             c += (double)gat_px(a.y, p.alpha, c0, toa);
             c += (double)gat_px(b.x, p.alpha, c0, toa);
             c += (double)gat_px(b.y, p.alpha, c0, toa);
-            v = (float)(c / 4.0);
+            v = (float)(c * 0.25);
         }
         g[ly][lx] = v;
     }
@@ -71,8 +82,8 @@ __global__ void __launch_bounds__(KBX *KBY) estimate_kernels_kernel(const float 
     const float cq = __fmaf_rn(T00, T11, -__fmul_rn(T01, T01));
     double delta = (double)__fmul_rn(bq, bq) - 4.0 * (double)cq;
     delta = (0.0 > delta) ? 0.0 : delta;
-    const double sq = sqrt(delta);
-    const double r1 = (-(double)bq + sq) / 2.0, r2 = (-(double)bq - sq) / 2.0;
+    const double sq = sqrt_fast(delta);
+    const double r1 = (-(double)bq + sq) * 0.5, r2 = (-(double)bq - sq) * 0.5;
     float l1, l2;
     if (fabs(r1) >= fabs(r2)) {
         l1 = (float)r1, l2 = (float)r2;
@@ -100,19 +111,19 @@ __global__ void __launch_bounds__(KBX *KBY) estimate_kernels_kernel(const float 
     }
     // compute_k (kernels.py:194-243)
     const double A = 1.0 + (double)__fsqrt_rn(__fdiv_rn(l1 - l2, l1 + l2));
-    double D = 1.0 - (double)__fsqrt_rn(l1) / p.D_tr + p.D_th;
+    double D = 1.0 - (double)__fsqrt_rn(l1) * p.inv_D_tr + p.D_th;
     D = (D > 0.0) ? D : 0.0;      // Numba max(0, x): NaN -> 0
     D = (D < 1.0) ? D : 1.0;
     double k1, k2;
     if (p.law == 0) {
         if (A > 1.95) {
-            k1 = 1.0 / p.k_shrink, k2 = p.k_stretch;
+            k1 = p.inv_k_shrink, k2 = p.k_stretch;
         } else {
             k1 = 1.0, k2 = 1.0;
         }
     } else {
-        k1 = 1.0 + A / 2.0 * (1.0 / p.k_shrink - 1.0);
-        k2 = 1.0 + A / 2.0 * (p.k_stretch - 1.0);
+        k1 = 1.0 + A * 0.5 * (p.inv_k_shrink - 1.0);
+        k2 = 1.0 + A * 0.5 * (p.k_stretch - 1.0);
     }
     const float kk1 = (float)(p.k_detail * ((1.0 - D) * k1 + D * p.k_denoise));
     const float kk2 = (float)(p.k_detail * ((1.0 - D) * k2 + D * p.k_denoise));
@@ -171,7 +182,8 @@ extern "C" int hhsr_estimate_kernels(const float *raw, int H, int W, double alph
     HHSR_REQUIRE(law == 0 || law == 1, "selection law must be 0 (hard_threshold) or 1 (linear)");
     HHSR_REQUIRE(((uintptr_t)raw % 8 == 0) && ((uintptr_t)covs % 16 == 0), "raw must be 8-byte, covs 16-byte aligned");
     const int h = H / 2, w = W / 2;
-    KernelParams p{alpha, beta, k_detail, k_denoise, D_th, D_tr, k_stretch, k_shrink, law};
+    HHSR_REQUIRE(D_tr != 0.0 && k_shrink != 0.0, "D_tr and k_shrink must be non-zero");
+    KernelParams p{alpha, beta, k_detail, k_denoise, D_th, D_tr, k_stretch, k_shrink, 1.0 / D_tr, 1.0 / k_shrink, law};
     dim3 block(KBX, KBY), grid(ceil_div(w, KBX), ceil_div(h, KBY));
     estimate_kernels_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(raw, H, W, h, w, p, covs);
     return launch_status("estimate_kernels");
