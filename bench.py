@@ -199,6 +199,21 @@ def run_cuda_arm(args, wl, wl_name):
     n, H, W, scale = wl["n"], wl["H"], wl["W"], wl["scale"]
     cfg = make_config(scale, H, W)
     hs, ws = round(scale * H), round(scale * W)
+    # the one reduction point: fused peer-memory kernel (default when it can be set up) or NCCL reduce-scatter
+    reduce_mode = args.reduce
+    if world > 1 and reduce_mode in ("auto", "p2p"):
+        try:
+            from handheld_super_resolution.distributed import P2PReduce
+            P2PReduce.get((hs, ws, 3))
+            reduce_mode = "p2p"
+        except Exception as e:      # no peer access / symmetric memory on this box
+            if args.reduce == "p2p":
+                raise
+            print("p2p reduction unavailable (%s); using NCCL reduce-scatter" % e, file=sys.stderr)
+            reduce_mode = "reduce_scatter"
+    elif reduce_mode == "auto":
+        reduce_mode = "reduce_scatter"
+    os.environ["HHSR_SHARD_REDUCE"] = reduce_mode
 
     burst_dev, _ = synth_burst(n, H, W, seed=0, device="cuda", as_numpy=False)      # same burst on every rank
     burst_host = torch.empty((n, H, W), dtype=torch.float32).pin_memory()
@@ -317,7 +332,9 @@ def run_cuda_arm(args, wl, wl_name):
             "value": out_mpix / (ms_res * 1e-3), "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (f64 sub-pixel positions)", "data": "synthetic",
-            "config": {"workload": wl_name, **wl, "tile_size": 32, "parallelism": "frames sharded over %d GPU(s), one NCCL sum" % world,
+            "config": {"workload": wl_name, **wl, "tile_size": 32, "parallelism": "frames sharded over %d GPU(s), %s" % (world, "single GPU" if world == 1 else (
+                           "one fused peer-memory kernel (NVLink pull + sum + merge_ref + divide, image gathered on rank 0)"
+                           if reduce_mode == "p2p" else "one NCCL reduce-scatter + all-gather of the image")),
                        "l2": "inputs per step (%.0f MB burst + %.0f MB accumulators) exceed the 126 MB L2; no flush needed"
                              % (n * H * W * 4 / 1e6, hs * ws * 24 / 1e6)},
             "e2e": {"value": out_mpix / (ms_e2e * 1e-3), "unit": "MPix/s", "ms_per_step": ms_e2e,
@@ -328,7 +345,7 @@ def run_cuda_arm(args, wl, wl_name):
                                    "h2d_bytes_per_step": int(n * H * W * 2),
                                    "note": "same call fed with 14-bit sensor counts (uint16), normalised on the device"}},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "accumulate_kernel (merge, one comp frame per launch)", "bound": "hbm",
+            "roofline": {"kernel": "accumulate_pow2_kernel (merge, one comp frame per launch)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_merge_ms,
                          "launches_timed": len(merge_ms)},
@@ -361,6 +378,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="20x12MP_s2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "reduce_scatter", "allreduce"],
+                    help="N > 1: how the frame-sharded accumulators are summed (auto = p2p when available)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

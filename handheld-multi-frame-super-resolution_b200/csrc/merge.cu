@@ -580,14 +580,25 @@ __global__ void __launch_bounds__(256, 2) accumulate_batch_kernel(MergeBatch b, 
 // reference promotes to float64 — float32-rounding-level differences, pinned by the goldens.
 // rows [row_begin, row_end) of the output are processed (frame-sharded runs normalise row slices).
 // ---------------------------------------------------------------------------------------------------------
+// Up to 16 peer accumulator pairs (frame-sharded runs): the kernel sums them in rank order while it normalises its
+// row slice, reading the peers' HBM over NVLink (peer-mapped pointers) — the reduction, merge_ref and divide in one pass.
+constexpr int kMaxPeers = 16;
+struct RefPeers {
+    const float *num[kMaxPeers], *den[kMaxPeers];
+    int n;             // 0: accumulate into (num, den) in place
+};
+
+// weight of one tap.  The reference's float32 accumulators keep weights down to the subnormal range (1e-45) and a
+// channel fed only by far taps of a narrow kernel is normalised from exactly those: evaluate them in float64.
+__device__ __noinline__ float tiny_weight(float z) { return (float)exp2((double)z); }
+__device__ __forceinline__ float ref_weight(float z) { return (z > -120.f) ? ex2_approx(z) : tiny_weight(z); }
+
+// One HR pixel of the reference frame: per-channel sums val/acc of its window; returns whether the accumulators are
+// to be overwritten (accumulated-robustness denoiser, merge.py:223-233).
 template <bool ISO>
-__global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__restrict__ raw, const float *__restrict__ covs,
-                                                             MergeGeom g, float *__restrict__ num, float *__restrict__ den,
-                                                             const double *__restrict__ acc_rob, int max_frame_count,
-                                                             int rad_max, float max_multiplier, int fuse_divide, int row_begin,
-                                                             int row_end) {
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
-    if (ox >= g.Ws || oy >= row_end) return;
+__device__ __forceinline__ bool ref_pixel(const float *__restrict__ raw, const float *__restrict__ covs, const MergeGeom &g, int ox,
+                                          int oy, const double *__restrict__ acc_rob, int max_frame_count, int rad_max,
+                                          float max_multiplier, float (&val)[3], float (&acc)[3]) {
     const float pos_y = (float)((double)oy / g.scale), pos_x = (float)((double)ox / g.scale);   // :113-114
     const float kS = -0.72134752044448170368f;   // -0.5 * log2(e)
     float qxx, qxy, qyy;
@@ -599,8 +610,8 @@ __global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__rest
         const int cx1 = min(fx0 + 1, g.cw - 1), cy1 = min(fy0 + 1, g.ch - 1);
         const float rx = gx - truncf(gx), ry = gy - truncf(gy);                                  // linalg.py:190-191
         const float4 *c4 = reinterpret_cast<const float4 *>(covs);
-        const float4 c00 = __ldg(c4 + (unsigned)fy0 * (unsigned)g.cw + fx0), c01 = __ldg(c4 + (unsigned)fy0 * (unsigned)g.cw + cx1);
-        const float4 c10 = __ldg(c4 + (unsigned)cy1 * (unsigned)g.cw + fx0), c11 = __ldg(c4 + (unsigned)cy1 * (unsigned)g.cw + cx1);
+        const float4 c00 = __ldg(c4 + (fy0 * g.cw + fx0)), c01 = __ldg(c4 + (fy0 * g.cw + cx1));
+        const float4 c10 = __ldg(c4 + (cy1 * g.cw + fx0)), c11 = __ldg(c4 + (cy1 * g.cw + cx1));
         const float w00 = (1.f - rx) * (1.f - ry), w01 = rx * (1.f - ry), w10 = (1.f - rx) * ry, w11 = rx * ry;
         const float m00 = fmaf(c11.x, w11, fmaf(c10.x, w10, fmaf(c01.x, w01, c00.x * w00)));
         const float m01 = fmaf(c11.y, w11, fmaf(c10.y, w10, fmaf(c01.y, w01, c00.y * w00)));
@@ -627,7 +638,40 @@ __global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__rest
         overwrite = la < (double)max_frame_count;
     }
     const int cx = (int)rintf(pos_x), cy = (int)rintf(pos_y);                                    // round half even
-    float val[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
+    val[0] = val[1] = val[2] = acc[0] = acc[1] = acc[2] = 0.f;
+    if (rad == 1 && cy >= 1 && cy <= g.H - 2 && cx >= 1 && cx <= g.W - 2) {
+        // interior 3x3 window: no bounds tests, partial sums per tap parity relative to the centre (compile-time
+        // indices), CFA channel of each partial resolved once
+        float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, a[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        const int o = cy * g.W + cx;
+#pragma unroll
+        for (int i = -1; i <= 1; ++i) {
+            const float dy = (float)(cy + i) - pos_y;
+            const float qy = qyy * dy * dy, qm = qxy * dy;
+            const float *row = raw + (o + i * g.W);
+#pragma unroll
+            for (int j = -1; j <= 1; ++j) {
+                const float c = __ldg(row + j);
+                const float dx = (float)(cx + j) - pos_x;
+                const float z = fminf(0.f, fmaf(fmaf(qxx, dx, qm), dx, qy));                     // max(0, y): NaN -> 0
+                const float w = ref_weight(z);
+                v[i & 1][j & 1] = fmaf(c, w, v[i & 1][j & 1]);
+                a[i & 1][j & 1] += w;
+            }
+        }
+#pragma unroll
+        for (int ry_ = 0; ry_ < 2; ++ry_)
+#pragma unroll
+            for (int rx_ = 0; rx_ < 2; ++rx_) {
+                const int chn = cfa_channel(g.cfa.packed, cy + ry_, cx + rx_);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    val[k] += (chn == k) ? v[ry_][rx_] : 0.f;
+                    acc[k] += (chn == k) ? a[ry_][rx_] : 0.f;
+                }
+            }
+        return overwrite;
+    }
     for (int i = -rad; i <= rad; ++i) {
         const int yy = cy + i;
         if (yy < 0 || yy >= g.H) continue;
@@ -637,12 +681,10 @@ __global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__rest
             const int xx = cx + j;
             if (xx < 0 || xx >= g.W) continue;
             const int chn = cfa_channel(g.cfa.packed, yy, xx);
-            const float c = __ldg(raw + (unsigned)yy * (unsigned)g.W + xx);
+            const float c = __ldg(raw + (yy * g.W + xx));
             const float dx = (float)xx - pos_x;
             const float z = fminf(0.f, fmaf(fmaf(qxx, dx, qm), dx, qy));                         // max(0, y): NaN -> 0
-            // The reference's float32 accumulators keep weights down to the subnormal range (1e-45) and a channel
-            // fed only by far taps of a narrow kernel is normalised from exactly those: evaluate them in float64.
-            const float w = (z > -120.f) ? ex2_approx(z) : (float)exp2((double)z);
+            const float w = ref_weight(z);
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 if (chn == k) {
@@ -651,14 +693,79 @@ __global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__rest
                 }
         }
     }
-    const size_t o = ((size_t)oy * g.Ws + ox) * 3;
+    return overwrite;
+}
+
+// VEC consecutive HR pixels of a row per thread (VEC = 4: float4 accesses of the 12-float slice).  Output:
+//   peers.n == 0 : num <- (num + val) [/ (den + acc) when fuse_divide], den <- den + acc, in place (merge.py:223-233);
+//   peers.n  > 0 : out_num <- (sum_p peers.num[p] + val) [/ ...]; den is not written (nobody reads it afterwards).
+template <bool ISO, int VEC>
+__global__ void __launch_bounds__(256) accumulate_ref_kernel(const float *__restrict__ raw, const float *__restrict__ covs,
+                                                             const __grid_constant__ MergeGeom g, float *num, float *den,
+                                                             const double *__restrict__ acc_rob, int max_frame_count,
+                                                             int rad_max, float max_multiplier, int fuse_divide, int row_begin,
+                                                             int row_end, const __grid_constant__ RefPeers peers, float *out_num) {
+    const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, oy = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox0 >= g.Ws || oy >= row_end) return;
+    const size_t o = ((size_t)oy * g.Ws + ox0) * 3;
+    float nn[VEC * 3], dd[VEC * 3];
+    // running sums of the accumulators first: the (remote) loads are in flight while the window math runs
+    if (peers.n == 0) {
+        if (VEC == 4) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float nn = overwrite ? val[k] : num[o + k] + val[k];
-        const float dd = overwrite ? acc[k] : den[o + k] + acc[k];
-        if (fuse_divide) nn = nn / dd;
-        num[o + k] = nn;
-        den[o + k] = dd;
+            for (int q = 0; q < 3; ++q) {
+                const float4 a = *reinterpret_cast<const float4 *>(num + o + 4 * q), c = *reinterpret_cast<const float4 *>(den + o + 4 * q);
+                nn[4 * q] = a.x, nn[4 * q + 1] = a.y, nn[4 * q + 2] = a.z, nn[4 * q + 3] = a.w;
+                dd[4 * q] = c.x, dd[4 * q + 1] = c.y, dd[4 * q + 2] = c.z, dd[4 * q + 3] = c.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) nn[k] = num[o + k], dd[k] = den[o + k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < VEC * 3; ++k) nn[k] = dd[k] = 0.f;
+        for (int p = 0; p < peers.n; ++p) {
+            const float *pn = peers.num[p] + o, *pd = peers.den[p] + o;
+            if (VEC == 4) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float4 a = *reinterpret_cast<const float4 *>(pn + 4 * q), c = *reinterpret_cast<const float4 *>(pd + 4 * q);
+                    nn[4 * q] += a.x, nn[4 * q + 1] += a.y, nn[4 * q + 2] += a.z, nn[4 * q + 3] += a.w;
+                    dd[4 * q] += c.x, dd[4 * q + 1] += c.y, dd[4 * q + 2] += c.z, dd[4 * q + 3] += c.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) nn[k] += pn[k], dd[k] += pd[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < VEC; ++p) {
+        float val[3], acc[3];
+        const bool overwrite = ref_pixel<ISO>(raw, covs, g, ox0 + p, oy, acc_rob, max_frame_count, rad_max, max_multiplier, val, acc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float n_ = overwrite ? val[k] : nn[3 * p + k] + val[k];
+            const float d_ = overwrite ? acc[k] : dd[3 * p + k] + acc[k];
+            if (fuse_divide) n_ = n_ / d_;
+            nn[3 * p + k] = n_, dd[3 * p + k] = d_;
+        }
+    }
+    float *on = peers.n == 0 ? num : out_num;
+    if (VEC == 4) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            *reinterpret_cast<float4 *>(on + o + 4 * q) = make_float4(nn[4 * q], nn[4 * q + 1], nn[4 * q + 2], nn[4 * q + 3]);
+            if (peers.n == 0)
+                *reinterpret_cast<float4 *>(den + o + 4 * q) = make_float4(dd[4 * q], dd[4 * q + 1], dd[4 * q + 2], dd[4 * q + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            on[o + k] = nn[k];
+            if (peers.n == 0) den[o + k] = dd[k];
+        }
     }
 }
 
@@ -791,6 +898,31 @@ extern "C" int hhsr_merge_accumulate(const float *raw, int H, int W, const float
                                        cfa_host, iso, stream);
 }
 
+static int launch_merge_ref(const float *raw, const float *covs, const MergeGeom &g, float *num, float *den, int iso,
+                            const double *acc_rob, int max_frame_count, int rad_max, double max_multiplier, int fuse_divide,
+                            int row_begin, int row_end, const RefPeers &peers, float *out_num, cudaStream_t st) {
+    dim3 block(32, 8);
+    const float mm = (float)max_multiplier;
+    if (g.Ws % 4 == 0) {
+        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(row_end - row_begin, 8));
+        if (iso)
+            accumulate_ref_kernel<true, 4><<<grid, block, 0, st>>>(raw, covs, g, num, den, acc_rob, max_frame_count, rad_max, mm,
+                                                                   fuse_divide, row_begin, row_end, peers, out_num);
+        else
+            accumulate_ref_kernel<false, 4><<<grid, block, 0, st>>>(raw, covs, g, num, den, acc_rob, max_frame_count, rad_max, mm,
+                                                                    fuse_divide, row_begin, row_end, peers, out_num);
+    } else {
+        dim3 grid(ceil_div(g.Ws, 32), ceil_div(row_end - row_begin, 8));
+        if (iso)
+            accumulate_ref_kernel<true, 1><<<grid, block, 0, st>>>(raw, covs, g, num, den, acc_rob, max_frame_count, rad_max, mm,
+                                                                   fuse_divide, row_begin, row_end, peers, out_num);
+        else
+            accumulate_ref_kernel<false, 1><<<grid, block, 0, st>>>(raw, covs, g, num, den, acc_rob, max_frame_count, rad_max, mm,
+                                                                    fuse_divide, row_begin, row_end, peers, out_num);
+    }
+    return launch_status("merge_ref");
+}
+
 extern "C" int hhsr_merge_ref(const float *raw, int H, int W, const float *covs, float *num, float *den, int Hs,
                               int Ws, double scale, const int *cfa_host, int iso, const double *acc_rob,
                               int max_frame_count, int rad_max, double max_multiplier, int fuse_divide, int row_begin,
@@ -800,16 +932,32 @@ extern "C" int hhsr_merge_ref(const float *raw, int H, int W, const float *covs,
     HHSR_REQUIRE(acc_rob == nullptr || (rad_max >= 0 && max_multiplier > 0.0), "rad_max >= 0 and max_multiplier > 0 required");
     HHSR_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= Hs, "row range must satisfy 0 <= begin < end <= Hs");
     MergeGeom g = make_geom(H, W, 0, 1, Hs, Ws, cfa_host, scale);
-    dim3 block(32, 8), grid(ceil_div(Ws, 32), ceil_div(row_end - row_begin, 8));
-    if (iso)
-        accumulate_ref_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(raw, covs, g, num, den, acc_rob, max_frame_count,
-                                                                             rad_max, (float)max_multiplier, fuse_divide,
-                                                                             row_begin, row_end);
-    else
-        accumulate_ref_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(raw, covs, g, num, den, acc_rob, max_frame_count,
-                                                                              rad_max, (float)max_multiplier, fuse_divide,
-                                                                              row_begin, row_end);
-    return launch_status("merge_ref");
+    RefPeers peers;
+    peers.n = 0;
+    return launch_merge_ref(raw, covs, g, num, den, iso, acc_rob, max_frame_count, rad_max, max_multiplier, fuse_divide,
+                            row_begin, row_end, peers, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int hhsr_reduce_merge_ref(const float *const *peer_nums, const float *const *peer_dens, int n_peers,
+                                     const float *raw, int H, int W, const float *covs, float *out_num, int Hs, int Ws,
+                                     double scale, const int *cfa_host, int iso, const double *acc_rob,
+                                     int max_frame_count, int rad_max, double max_multiplier, int fuse_divide,
+                                     int row_begin, int row_end, hhsr_stream_t stream) {
+    HHSR_REQUIRE(peer_nums && peer_dens && n_peers >= 1 && n_peers <= kMaxPeers, "1 to 16 peer accumulator pairs required");
+    if (int e = check_merge_args(raw, out_num, out_num, H, W, Hs, Ws, scale, cfa_host)) return e;
+    HHSR_REQUIRE(iso || (covs && (uintptr_t)covs % 16 == 0), "covs required (16-byte aligned) for the steerable kernel");
+    HHSR_REQUIRE(acc_rob == nullptr || (rad_max >= 0 && max_multiplier > 0.0), "rad_max >= 0 and max_multiplier > 0 required");
+    HHSR_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= Hs, "row range must satisfy 0 <= begin < end <= Hs");
+    MergeGeom g = make_geom(H, W, 0, 1, Hs, Ws, cfa_host, scale);
+    RefPeers peers;
+    peers.n = n_peers;
+    for (int p = 0; p < n_peers; ++p) {
+        HHSR_REQUIRE(peer_nums[p] && peer_dens[p], "null peer pointer");
+        HHSR_REQUIRE((uintptr_t)peer_nums[p] % 16 == 0 && (uintptr_t)peer_dens[p] % 16 == 0, "peer accumulators must be 16-byte aligned");
+        peers.num[p] = peer_nums[p], peers.den[p] = peer_dens[p];
+    }
+    return launch_merge_ref(raw, covs, g, nullptr, nullptr, iso, acc_rob, max_frame_count, rad_max, max_multiplier, fuse_divide,
+                            row_begin, row_end, peers, out_num, (cudaStream_t)stream);
 }
 
 extern "C" int hhsr_divide(float *num, const float *den, size_t n, hhsr_stream_t stream) {

@@ -55,10 +55,71 @@ def reduce_scatter_accumulators(num, den, acc_rob=None, group=None):
     return (rank * rows, (rank + 1) * rows), gather
 
 
+class P2PReduce:
+    """The reduction point as ONE kernel over NVLink peer memory (mode "p2p"): every rank keeps its private num/den in
+    a symmetric-memory buffer (torch.distributed._symmetric_memory: the same allocation mapped into every rank's
+    address space); after a device-side barrier rank g runs hhsr_reduce_merge_ref on its slice of output rows — it
+    pulls the G partial accumulators of that slice straight from the peers' HBM, adds the reference frame, divides,
+    and stores the finished pixels into rank 0's buffer.  No NCCL pass, no separate merge_ref / divide pass, and the
+    1/G slices travel once.  Only rank 0 ends up with the whole image (a gather, not an all-gather).
+    Buffers and the rendezvous (~2 s) are cached per output shape."""
+    _cache = {}
+
+    def __init__(self, shape, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.shape = tuple(shape)
+        n = 1
+        for d in self.shape:
+            n *= d
+        self.numel = n
+        self.flat = symm_mem.empty((2 * n,), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm_mem.rendezvous(self.flat, self.group)
+        self.num = self.flat[:n].view(self.shape)
+        self.den = self.flat[n:].view(self.shape)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    @classmethod
+    def get(cls, shape, group=None):
+        key = (tuple(shape), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(shape, group)
+        return cls._cache[key]
+
+    def rows(self):
+        Hs = self.shape[0]
+        return (self.rank * Hs) // self.world, ((self.rank + 1) * Hs) // self.world
+
+    def finalize(self, ref_img, covs, num, den, acc_rob, cfa_pattern, config):
+        import ctypes as C
+        from . import _lib
+        assert num.data_ptr() == self.num.data_ptr() and den.data_ptr() == self.den.data_ptr()
+        ard = config.accumulated_robustness_denoiser
+        if acc_rob is not None:
+            dist.all_reduce(acc_rob, op=dist.ReduceOp.SUM, group=self.group)
+        if ard.enabled:
+            acc, rad_max, max_mult, max_fc = acc_rob, int(ard.merge.rad_max), float(ard.merge.max_multiplier), int(ard.merge.max_frame_count)
+        else:
+            acc, rad_max, max_mult, max_fc = None, 0, 0.0, 0
+        self.hdl.barrier(channel=0)                 # every rank has finished accumulating its frames
+        H, W = ref_img.shape
+        iso = config.merging.kernel == "iso"
+        nums = (C.c_void_p * self.world)(*self.peer_ptrs)
+        dens = (C.c_void_p * self.world)(*[p + 4 * self.numel for p in self.peer_ptrs])
+        r0, r1 = self.rows()
+        _lib.call("hhsr_reduce_merge_ref", nums, dens, self.world, _lib.ptr(ref_img), H, W, _lib.ptr(None if iso else covs),
+                  C.c_void_p(self.peer_ptrs[0]), self.shape[0], self.shape[1], float(config.scale),
+                  _lib.cfa_array(cfa_pattern), int(iso), _lib.ptr(acc), max_fc, rad_max, max_mult, 1, r0, r1, _lib.stream())
+        self.hdl.barrier(channel=1)                 # all slices delivered; peers may reuse their accumulators
+        return num                                  # the whole image on rank 0 only
+
+
 def main_sharded(ref_img, comp_imgs, config, group=None, mode=None):
     """main() with the comp frames of this rank only and one sum of the accumulators at the reduction point
-    (mode "reduce_scatter", default, or "allreduce"; env HHSR_SHARD_REDUCE overrides).  Every rank returns the full
-    normalised image (identical up to float32 summation order)."""
+    (mode "reduce_scatter", default, "allreduce", or "p2p" — the fused peer-memory kernel, see P2PReduce; env
+    HHSR_SHARD_REDUCE overrides).  With the NCCL modes every rank returns the full normalised image (identical up to
+    float32 summation order); with "p2p" only rank 0 does."""
     import os
     from .super_resolution import main
     if dist.is_available() and dist.is_initialized():
@@ -67,6 +128,11 @@ def main_sharded(ref_img, comp_imgs, config, group=None, mode=None):
         rank, world = 0, 1
     mode = mode or os.environ.get("HHSR_SHARD_REDUCE", "reduce_scatter")
     ids = shard_frames(len(comp_imgs), rank, world)
+    if mode == "p2p" and world > 1:
+        H, W = ref_img.shape
+        s = config.scale
+        red = P2PReduce.get((round(s * H), round(s * W), 3), group)
+        return main(ref_img, comp_imgs, config, frame_ids=ids, accumulators=(red.num, red.den), finalize_fn=red.finalize)
     if mode == "allreduce":
         fn = lambda n, d, a: allreduce_accumulators(n, d, a, group)   # noqa: E731
     else:

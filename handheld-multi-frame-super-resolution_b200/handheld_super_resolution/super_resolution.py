@@ -131,7 +131,7 @@ class FrameFeeder:
             self.free_ev[item[2]] = ev
 
 
-def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
+def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulators=None, finalize_fn=None):
     """Device pipeline (super_resolution.py:41-200).
 
     ref_img [H,W], comp_imgs [N-1,H,W]: float32 host arrays (numpy / pinned torch) or CUDA tensors.
@@ -139,7 +139,9 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
 
     B200 additions (optional, used by the distributed driver): `frame_ids` restricts the comp loop to a subset of
     frames (frame sharding) and `reduce_fn(num, den, acc_rob)` is called once after the loop — the one natural
-    reduction point of the pipeline."""
+    reduction point of the pipeline.  `accumulators=(num, den)` supplies caller-owned accumulators
+    (e.g. peer-mapped symmetric memory; zeroed here) and `finalize_fn(ref_img, covs, num, den, acc_rob, cfa, config)`
+    replaces reduction + merge_ref + divide by one fused step (distributed.P2PReduce) and returns the image."""
     verbose_2 = config.verbose >= 2
     grey_method = config.grey_method
     if config.mode != "bayer":
@@ -177,8 +179,13 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
     H, W = cuda_ref_img.shape
     scale = config.scale
     output_size = (round(scale * H), round(scale * W))
-    num = torch.zeros((*output_size, 3), dtype=torch.float32, device=dev)
-    den = torch.zeros((*output_size, 3), dtype=torch.float32, device=dev)
+    if accumulators is not None:
+        num, den = accumulators
+        assert tuple(num.shape) == (*output_size, 3) and tuple(den.shape) == (*output_size, 3)
+        num.zero_(), den.zero_()
+    else:
+        num = torch.zeros((*output_size, 3), dtype=torch.float32, device=dev)
+        den = torch.zeros((*output_size, 3), dtype=torch.float32, device=dev)
     accumulated_r = torch.zeros((H, W), dtype=torch.float64, device=dev) if accumulate_r else None
 
     _mark("ref_side")
@@ -234,6 +241,13 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None):
     # may hand back the slice of output rows this rank has to normalise plus a callable that re-assembles the image
     rows, gather_fn = None, None
     _mark("frames")
+    if finalize_fn is not None:
+        covs = estimate_kernels_(cuda_ref_img, config)
+        num = finalize_fn(cuda_ref_img, covs, num, den, accumulated_r, cfa_pattern, config)
+        _mark("fused_reduce_merge_ref")
+        if accumulate_r:
+            debug_dict["accumulated robustness"] = accumulated_r
+        return num, debug_dict
     if reduce_fn is not None:
         res = reduce_fn(num, den, accumulated_r)
         if res is not None:

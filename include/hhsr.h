@@ -141,6 +141,16 @@ int hhsr_merge_ref(const float *raw, int H, int W, const float *covs, float *num
                    int rad_max, double max_multiplier, int fuse_divide, int row_begin, int row_end,
                    hhsr_stream_t stream);
 
+/* ---- frame-sharded runs (a B200 addition, the reference is single-GPU): the one reduction point of
+ * the pipeline fused with merge_ref and divide.  peer_nums/peer_dens: HOST arrays of n_peers DEVICE pointers to the
+ * ranks' private accumulators [Hs][Ws][3] (peer-mapped over NVLink, e.g. torch symmetric memory), summed in array
+ * order; rows [row_begin, row_end) of  (sum_p num_p + ref) / (sum_p den_p + ref)  are written to out_num (which may
+ * itself be a peer pointer, e.g. rank 0's image).  Remaining arguments as hhsr_merge_ref. */
+int hhsr_reduce_merge_ref(const float *const *peer_nums, const float *const *peer_dens, int n_peers, const float *raw,
+                          int H, int W, const float *covs, float *out_num, int Hs, int Ws, double scale,
+                          const int *cfa_host, int iso, const double *acc_rob, int max_frame_count, int rad_max,
+                          double max_multiplier, int fuse_divide, int row_begin, int row_end, hhsr_stream_t stream);
+
 /* ---- element-wise helpers (utils.py:62-120) */
 int hhsr_divide(float *num, const float *den, size_t n, hhsr_stream_t stream);
 int hhsr_add_f64_f32(double *A, const float *B, size_t n, hhsr_stream_t stream);
