@@ -244,6 +244,98 @@ __global__ void ref_noise_terms_kernel(const float *__restrict__ ref_means, cons
     }
 }
 
+// Reference-side statistics in ONE pass (init_robustness + the reference part of the noise model): x2 Dodgson
+// upsampling (no flow) of the guide means and variances [3][h][w] and, from them, the noise terms — the upsampled
+// variances are consumed on the fly and only written when the caller wants the reference's (means, stds) pair.
+// One thread = the 2x2 raw pixels of one guide pixel.  Without flow the sampling position is (y + 0.5)/2 - 0.5, i.e.
+// guide row y >> 1 -/+ 0.25 for even/odd y: three taps around the nearest guide pixel with the constant Dodgson weights
+// q(-0.75), q(0.25), q(1.25) = 0.1875, 0.875, -0.0625 (sum 1; reversed for odd pixels).  Guide pixels on the border ring
+// (clamped taps, the +inf rule for y = 0 / x = 0) take the per-pixel sampler of upscale_warp_kernel.
+__global__ void __launch_bounds__(RBX *RBY) ref_stats_terms_kernel(const float *__restrict__ gm, const float *__restrict__ gv, int h,
+                                                                   int w, const float2 *__restrict__ table, int n_curve,
+                                                                   float *__restrict__ ref_means, float *__restrict__ ref_vars,
+                                                                   float *__restrict__ terms) {
+    const int gx = blockIdx.x * RBX + threadIdx.x, gy = blockIdx.y * RBY + threadIdx.y;
+    if (gx >= w || gy >= h) return;
+    const int H = 2 * h, W = 2 * w;
+    const size_t plane = (size_t)H * W, lplane = (size_t)h * w;
+    float m[2][2][3], v[2][2][3];      // [row parity][col parity][channel]
+    bool ok[2][2] = {{true, true}, {true, true}};
+    if (gy >= 1 && gy <= h - 2 && gx >= 1 && gx <= w - 2) {
+        const float wk[2][3] = {{0.1875f, 0.875f, -0.0625f}, {-0.0625f, 0.875f, 0.1875f}};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int s_ = 0; s_ < 2; ++s_) {
+                const float *src = (s_ ? gv : gm) + c * lplane + (size_t)(gy - 1) * w + (gx - 1);
+                float t[3][3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) t[i][j] = __ldg(src + i * w + j);
+#pragma unroll
+                for (int py = 0; py < 2; ++py) {
+                    float col[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) col[j] = fmaf(t[2][j], wk[py][2], fmaf(t[1][j], wk[py][1], t[0][j] * wk[py][0]));
+#pragma unroll
+                    for (int px = 0; px < 2; ++px) {
+                        const float r = fmaf(col[2], wk[px][2], fmaf(col[1], wk[px][1], col[0] * wk[px][0]));
+                        if (s_) v[py][px][c] = r; else m[py][px][c] = r;
+                    }
+                }
+            }
+    } else {
+#pragma unroll 1
+        for (int py = 0; py < 2; ++py)
+#pragma unroll 1
+            for (int px = 0; px < 2; ++px) {
+                const Axis ay = dodgson_axis(2 * gy + py, 0.f, h), ax = dodgson_axis(2 * gx + px, 0.f, w);
+                ok[py][px] = ay.ok && ax.ok;
+                float am[3] = {0.f, 0.f, 0.f}, av[3] = {0.f, 0.f, 0.f}, wacc = 0.f;
+                if (ok[py][px]) {
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) {
+                            const float wgt = ay.w[i] * ax.w[j];
+                            const size_t q = (size_t)ay.i[i] * w + ax.i[j];
+                            for (int c = 0; c < 3; ++c) {
+                                am[c] = fmaf(__ldg(gm + q + c * lplane), wgt, am[c]);
+                                av[c] = fmaf(__ldg(gv + q + c * lplane), wgt, av[c]);
+                            }
+                            wacc += wgt;
+                        }
+                }
+                for (int c = 0; c < 3; ++c) {
+                    m[py][px][c] = ok[py][px] ? am[c] / wacc : INFINITY;      // out of the guide image: +inf (robustness.py:383-391)
+                    v[py][px][c] = ok[py][px] ? av[c] / wacc : INFINITY;
+                }
+            }
+    }
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+        const size_t o = (size_t)(2 * gy + py) * W + 2 * gx;
+        float sig[2] = {0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float dt[2];
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                const float brightness = m[py][px][c];
+                int id = 0;
+                if (isfinite(brightness)) id = (int)llrint(1000.0 * (double)brightness);   // robustness.py:519
+                id = min(max(id, 0), n_curve - 1);
+                const float2 t = __ldg(table + id);
+                sig[px] += fmaxf(v[py][px][c], t.x);                                       // :524
+                dt[px] = t.y;
+            }
+            *reinterpret_cast<float2 *>(ref_means + o + c * plane) = make_float2(m[py][0][c], m[py][1][c]);
+            *reinterpret_cast<float2 *>(terms + o + c * plane) = make_float2(dt[0], dt[1]);
+            if (ref_vars) *reinterpret_cast<float2 *>(ref_vars + o + c * plane) = make_float2(v[py][0][c], v[py][1][c]);
+        }
+        *reinterpret_cast<float2 *>(terms + o + 3 * plane) = make_float2(sig[0], sig[1]);
+    }
+}
+
 // Noise model + threshold for one pixel given its warped comp means (robustness.py:452-462, 504-533, 626-639)
 __device__ __forceinline__ float robustness_finish(float d_sq, float sigma_sq, float S, double t) {
     const float e = expf(-__fdividef(d_sq, sigma_sq));                      // math.exp(float32), :638
@@ -564,6 +656,19 @@ extern "C" int hhsr_robustness_ref_terms(const float *ref_means, const float *re
                                                                             reinterpret_cast<const float2 *>(noise_table),
                                                                             n_curve, terms);
     return launch_status("robustness_ref_terms");
+}
+
+extern "C" int hhsr_ref_stats_terms(const float *guide_means, const float *guide_vars, int h, int w, const float *noise_table,
+                                    int n_curve, float *ref_means, float *ref_vars, float *terms, hhsr_stream_t stream) {
+    HHSR_REQUIRE(guide_means && guide_vars && noise_table && ref_means && terms, "null pointer");
+    HHSR_REQUIRE(h >= 1 && w >= 1 && n_curve > 0, "non-positive size");
+    HHSR_REQUIRE((uintptr_t)noise_table % 8 == 0 && (uintptr_t)ref_means % 8 == 0 && (uintptr_t)terms % 8 == 0 &&
+                     (uintptr_t)ref_vars % 8 == 0, "outputs and noise table must be 8-byte aligned");
+    dim3 block(RBX, RBY), grid(ceil_div(w, RBX), ceil_div(h, RBY));
+    ref_stats_terms_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(guide_means, guide_vars, h, w,
+                                                                    reinterpret_cast<const float2 *>(noise_table), n_curve,
+                                                                    ref_means, ref_vars, terms);
+    return launch_status("ref_stats_terms");
 }
 
 extern "C" int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_terms, int H, int W,

@@ -32,6 +32,7 @@ SIGNATURES = {
     "hhsr_guide_stats": [_P, _I, _I, _IP, _DP, _P, _P, _P],
     "hhsr_upscale_warp_stats": [_P, _I, _I, _P, _I, _I, _I, _P, _P],
     "hhsr_noise_table": [_P, _P, _I, _P, _P],
+    "hhsr_ref_stats_terms": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P],
     "hhsr_robustness_ref_terms": [_P, _P, _I, _I, _P, _I, _P, _P],
     "hhsr_robustness": [_P, _P, _P, _I, _I, _P, _I, _I, _I, _D, _D, _D, _D, _P, _P],
     "hhsr_local_min5": [_P, _I, _I, _P, _P, _P],

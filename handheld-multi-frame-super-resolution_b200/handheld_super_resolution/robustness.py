@@ -33,15 +33,30 @@ def upscale_warp_stats(local_stats, tile_size=None, flow=None):
     return out
 
 
-def init_robustness(ref_img, cfa_pattern, white_balance, config):
+def init_robustness(ref_img, cfa_pattern, white_balance, config, noise_model=None, need_stds=True):
     """Local statistics of the reference frame, upsampled to raw resolution (robustness.py:23-76).
-    Returns (local_means, local_stds) [3, H, W] — `local_stds` holds variances, like the reference."""
+    Returns (local_means, local_stds) [3, H, W] — `local_stds` holds variances, like the reference.
+
+    B200 addition: when `noise_model` (the curves or a table from noise_table()) is given, the upsampling of both
+    statistics and the reference-side noise terms (see ref_noise_terms) come from ONE launch and the terms are cached
+    on `local_means` for compute_robustness; with need_stds=False the upsampled variances are not even written
+    (local_stds is None; main() uses this)."""
     if not config.robustness.enabled:
         return None, None
     if config.mode != "bayer":
         raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
     means, vars_ = compute_guide_stats(ref_img, cfa_pattern, white_balance)
-    return upscale_warp_stats(means), upscale_warp_stats(vars_)
+    if noise_model is None:
+        return upscale_warp_stats(means), upscale_warp_stats(vars_)
+    table = noise_table(noise_model)
+    _, h, w = means.shape
+    up_means = torch.empty((3, 2 * h, 2 * w), dtype=torch.float32, device=means.device)
+    up_vars = torch.empty_like(up_means) if need_stds else None
+    terms = torch.empty((4, 2 * h, 2 * w), dtype=torch.float32, device=means.device)
+    _lib.call("hhsr_ref_stats_terms", _lib.ptr(means), _lib.ptr(vars_), h, w, _lib.ptr(table), table.shape[0],
+              _lib.ptr(up_means), _lib.ptr(up_vars), _lib.ptr(terms), _lib.stream())
+    up_means._hhsr_noise_terms = (("fused", table.data_ptr()), terms, table)
+    return up_means, up_vars
 
 
 def noise_table(noise_model):
@@ -62,8 +77,13 @@ def ref_noise_terms(ref_local_means, ref_local_stds, table):
     """Reference-side part of the noise model (robustness.py:504-533): [4, H, W] = (d_t^2 per channel, sum of
     max(sigma_p^2, sigma_t^2)).  Depends on the reference frame only, so it is built once per burst and cached on the
     `ref_local_means` tensor (the reference recomputes it for every comp frame)."""
-    key = (ref_local_stds.data_ptr(), table.data_ptr(), ref_local_means._version, ref_local_stds._version)
     cached = getattr(ref_local_means, "_hhsr_noise_terms", None)
+    if cached is not None and cached[0] == ("fused", table.data_ptr()):      # built by init_robustness(noise_model=...)
+        return cached[1]
+    if ref_local_stds is None:
+        raise ValueError("ref_local_stds is required unless init_robustness() was given the noise model")
+    ref_local_stds = _lib.as_device(ref_local_stds)
+    key = (ref_local_stds.data_ptr(), table.data_ptr(), ref_local_means._version, ref_local_stds._version)
     if cached is not None and cached[0] == key:
         return cached[1]
     _, H, W = ref_local_means.shape
@@ -101,7 +121,7 @@ def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pat
     comp_means, _ = compute_guide_stats(comp_img, cfa_pattern, white_balance, need_vars=False)
     R = torch.empty((H, W), dtype=torch.float32, device=comp_img.device)
     ref_local_means = _lib.as_device(ref_local_means)
-    terms = ref_noise_terms(ref_local_means, _lib.as_device(ref_local_stds), table)
+    terms = ref_noise_terms(ref_local_means, ref_local_stds, table)
     _lib.call("hhsr_robustness", _lib.ptr(comp_means), _lib.ptr(ref_local_means), _lib.ptr(terms), H, W,
               _lib.ptr(flows), flows.shape[0], flows.shape[1], int(ts),
               float(tun.t), float(tun.s1), float(tun.s2), float(tun.Mt), _lib.ptr(R), _lib.stream())

@@ -174,7 +174,8 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
 
     cuda_ref_grey = compute_grey_images(cuda_ref_img, grey_method)
     ref_pyramid, tyled_pyr, ref_tiled_fft, ref_gradx, ref_grady, ref_hessian = init_alignment_(cuda_ref_grey, config)
-    ref_local_means, ref_local_stds = init_robustness_(cuda_ref_img, cfa_pattern, white_balance, config)
+    ref_local_means, ref_local_stds = init_robustness_(cuda_ref_img, cfa_pattern, white_balance, config,
+                                                       noise_model=noise_tab, need_stds=False)
 
     H, W = cuda_ref_img.shape
     scale = config.scale

@@ -105,6 +105,11 @@ int hhsr_noise_table(const double *std_curve, const double *diff_curve, int n_cu
  * ref_means/ref_vars: [3][H][W] from hhsr_upscale_warp_stats; noise_table from hhsr_noise_table. */
 int hhsr_robustness_ref_terms(const float *ref_means, const float *ref_vars, int H, int W, const float *noise_table,
                               int n_curve, float *terms, hhsr_stream_t stream);
+/* the three calls above in one pass for the reference frame (init_robustness, robustness.py:23-76, + the reference
+ * part of the noise model): guide_means/guide_vars [3][h][w] from hhsr_guide_stats -> ref_means [3][2h][2w],
+ * terms [4][2h][2w]; ref_vars [3][2h][2w] is only written when non-NULL. */
+int hhsr_ref_stats_terms(const float *guide_means, const float *guide_vars, int h, int w, const float *noise_table,
+                         int n_curve, float *ref_means, float *ref_vars, float *terms, hhsr_stream_t stream);
 /* fused per-pixel robustness (robustness.py:421-639): warped Dodgson upsampling of the comp guide means,
  * |mean difference|, noise-model shrinkage, flow-irregularity factor S and threshold -> R [H][W].
  * ref_means: [3][H][W] from hhsr_upscale_warp_stats; ref_terms: [4][H][W] from hhsr_robustness_ref_terms. */

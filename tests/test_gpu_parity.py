@@ -232,6 +232,53 @@ def test_compute_robustness(tiny, stage):
     assert torch.all(RB.compute_robustness(dev(stage["raw"]), m, s, dev(stage["flow_irreg"]), CFA, WB, (std, diff), cfg) == 1)
 
 
+def test_init_robustness_fused_equals_stage_chain():
+    """init_robustness(noise_model=...) — one launch for the upsampled reference statistics and noise terms — against
+    the stage chain (two hhsr_upscale_warp_stats + hhsr_robustness_ref_terms): same taps, constant-weight separable
+    blend instead of 9 weighted taps -> float32 rounding (a 1-ulp change of a mean may move its brightness bin)."""
+    from handheld_super_resolution import robustness as RB
+    from handheld_super_resolution.synthetic import synth_burst
+    for H, W in [(96, 128), (1000, 1504)]:
+        burst, _ = synth_burst(1, H, W, seed=13, device="cuda", as_numpy=False)
+        cfg = attr_cfg(scale=2)
+        table = RB.noise_table(curves())
+        m0, s0 = RB.init_robustness(burst[0], CFA, WB, cfg)
+        t0 = RB.ref_noise_terms(m0, s0, table)
+        m1, s1 = RB.init_robustness(burst[0], CFA, WB, cfg, noise_model=table)
+        t1 = RB.ref_noise_terms(m1, None, table)
+        m2, s2 = RB.init_robustness(burst[0], CFA, WB, cfg, noise_model=table, need_stds=False)
+        assert s2 is None and torch.equal(torch.nan_to_num(m1, posinf=7.0), torch.nan_to_num(m2, posinf=7.0))
+        for a, b in ((m0, m1), (s0, s1)):
+            assert torch.equal(torch.isinf(a), torch.isinf(b))
+            fin = torch.isfinite(a)
+            assert (a[fin] - b[fin]).abs().max().item() < 2e-7
+        fin = torch.isfinite(m0).all(0)
+        rel = ((t0 - t1).abs() / t0.abs().clamp_min(1e-12))[:, fin]
+        assert (rel > 1e-5).float().mean().item() < 1e-3 and rel.max().item() < 5e-2
+
+
+def test_reduce_merge_ref_equals_sum_then_merge_ref(stage):
+    """hhsr_reduce_merge_ref (the frame-sharded reduction point fused with merge_ref and divide) with three local
+    'peer' accumulator pairs against: sum the pairs in order, then merge_ref(fuse_divide) — bit-identical."""
+    import ctypes as C
+    from handheld_super_resolution import _lib, merge as MG
+    cfg = attr_cfg(scale=2)
+    raw, covs = dev(stage["ref"]), dev(stage["covs_ref"])
+    H, W = raw.shape
+    g = torch.Generator(device="cuda").manual_seed(2)
+    nums = [torch.rand((2 * H, 2 * W, 3), device="cuda", generator=g) for _ in range(3)]
+    dens = [torch.rand((2 * H, 2 * W, 3), device="cuda", generator=g) + 0.5 for _ in range(3)]
+    n_want, d_want = (nums[0] + nums[1]) + nums[2], (dens[0] + dens[1]) + dens[2]
+    MG.merge_ref(raw, covs, n_want, d_want, CFA, cfg, fuse_divide=True)
+    out = nums[0]     # like the real run: the image is delivered into the first rank's accumulator
+    Hs = 2 * H
+    for r0, r1 in ((0, Hs // 3), (Hs // 3, Hs)):
+        _lib.call("hhsr_reduce_merge_ref", (C.c_void_p * 3)(*[t.data_ptr() for t in nums]),
+                  (C.c_void_p * 3)(*[t.data_ptr() for t in dens]), 3, _lib.ptr(raw), H, W, _lib.ptr(covs), _lib.ptr(out), Hs,
+                  2 * W, 2.0, _lib.cfa_array(CFA), 0, None, 0, 0, 0.0, 1, r0, r1, _lib.stream())
+    assert torch.equal(torch.nan_to_num(out), torch.nan_to_num(n_want))
+
+
 def test_robustness_tile_path_equals_pixel_path():
     """The block-uniform fast path of hhsr_robustness (parity weight sets, separable 4x5 window) against the
     per-pixel path on a 12 MP frame with random sub-pixel flows: same taps and weights, different summation order
