@@ -295,7 +295,9 @@ __device__ __forceinline__ float merge_hr_pixel(const MergeFrame &f, const Merge
 // of one row.  The accumulator slice (2 x 3 float4) is prefetched into L2 at entry and only loaded after the
 // gathers/weights are done: its registers are not live during the math (more resident warps) while its HBM latency
 // still overlaps the math.  `num += val` with val the per-frame sum, exactly as the reference.
-template <bool ISO, int VEC>
+// STORE: the accumulators are INITIALISED with this frame's contribution (0 + r * x, same flush-to-zero addition) instead
+// of being read and updated — the first comp frame of a burst then needs no zero-filled accumulators.
+template <bool ISO, int VEC, bool STORE = false>
 __device__ __forceinline__ void accumulate_thread(const MergeFrame &f, const MergeGeom &g, float *__restrict__ num,
                                                   float *__restrict__ den, int hr_i, int j0) {
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
@@ -317,8 +319,11 @@ __device__ __forceinline__ void accumulate_thread(const MergeFrame &f, const Mer
         const float *nf = &n[0][0], *df = &d[0][0];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            float4 a = *reinterpret_cast<const float4 *>(num + base + 4 * q);
-            float4 c = *reinterpret_cast<const float4 *>(den + base + 4 * q);
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+            if (!STORE) {
+                a = *reinterpret_cast<const float4 *>(num + base + 4 * q);
+                c = *reinterpret_cast<const float4 *>(den + base + 4 * q);
+            }
             a.x = add_ftz(a.x, rr[(4 * q) / 3], nf[4 * q]), a.y = add_ftz(a.y, rr[(4 * q + 1) / 3], nf[4 * q + 1]);
             a.z = add_ftz(a.z, rr[(4 * q + 2) / 3], nf[4 * q + 2]), a.w = add_ftz(a.w, rr[(4 * q + 3) / 3], nf[4 * q + 3]);
             c.x = add_ftz(c.x, rr[(4 * q) / 3], df[4 * q]), c.y = add_ftz(c.y, rr[(4 * q + 1) / 3], df[4 * q + 1]);
@@ -332,26 +337,26 @@ __device__ __forceinline__ void accumulate_thread(const MergeFrame &f, const Mer
             if (j0 + p < g.Ws)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    num[base + p * 3 + c] = add_ftz(num[base + p * 3 + c], rr[p], n[p][c]);
-                    den[base + p * 3 + c] = add_ftz(den[base + p * 3 + c], rr[p], d[p][c]);
+                    num[base + p * 3 + c] = add_ftz(STORE ? 0.f : num[base + p * 3 + c], rr[p], n[p][c]);
+                    den[base + p * 3 + c] = add_ftz(STORE ? 0.f : den[base + p * 3 + c], rr[p], d[p][c]);
                 }
     }
 }
 
-template <bool ISO, int VEC>
+template <bool ISO, int VEC, bool STORE>
 __global__ void __launch_bounds__(256, HHSR_MERGE_MINBLOCKS) accumulate_kernel(MergeFrame f, MergeGeom g, float *__restrict__ num,
                                                                                 float *__restrict__ den) {
     const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (hr_i >= g.Hs || j0 >= g.Ws) return;
-    if (VEC == 4 && (threadIdx.x & 1) == 0) {   // 2 threads share 96 B = at most 2 lines per accumulator
+    if (!STORE && VEC == 4 && (threadIdx.x & 1) == 0) {   // 2 threads share 96 B = at most 2 lines per accumulator
         const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
         prefetch_l2(num + base);
         prefetch_l2(den + base);
         prefetch_l2(num + base + 23);
         prefetch_l2(den + base + 23);
     }
-    accumulate_thread<ISO, VEC>(f, g, num, den, hr_i, j0);
+    accumulate_thread<ISO, VEC, STORE>(f, g, num, den, hr_i, j0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -370,18 +375,23 @@ __device__ __forceinline__ void split_q(float q, float ff, int &l, float &t) {
     t = (q - (float)l) + ff;
 }
 
-template <bool ISO>
+template <bool ISO, bool STORE>
 __device__ __noinline__ void accumulate_thread_border(const MergeFrame *f, const MergeGeom *g, float *num, float *den, int hr_i,
                                                       int j0) {
-    accumulate_thread<ISO, 4>(*f, *g, num, den, hr_i, j0);
+    accumulate_thread<ISO, 4, STORE>(*f, *g, num, den, hr_i, j0);
 }
 
 // p[0..3] += r_k * x_k as ONE fire-and-forget 16-byte reduction performed by the L2 (REDG.E.ADD.F32x4): the SM never
 // loads the accumulators, so their HBM/L2 latency is off the warps' critical path.  Each address receives exactly one
 // reduction per launch (deterministic).  Like every f32 atomic the L2 adder flushes subnormals (add.ftz); the generic
 // kernels use add_ftz() below so that all merge kernels still agree bit for bit.
+template <bool STORE>
 __device__ __forceinline__ void rmw4(float *__restrict__ p, float r0, float a, float r1, float b, float r2, float c, float r3,
                                      float d) {
+    if (STORE) {   // first frame of a burst: initialise instead of accumulate (0 + r * x with the same flush-to-zero add)
+        *reinterpret_cast<float4 *>(p) = make_float4(add_ftz(0.f, r0, a), add_ftz(0.f, r1, b), add_ftz(0.f, r2, c), add_ftz(0.f, r3, d));
+        return;
+    }
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r0 * a), "f"(r1 * b), "f"(r2 * c), "f"(r3 * d)
                  : "memory");
 }
@@ -419,7 +429,7 @@ __device__ __forceinline__ void resolve_rggb(bool sy, bool sx, const float (&v)[
     out[0] = R, out[1] = G, out[2] = B;
 }
 
-template <bool ISO, int K>
+template <bool ISO, int K, bool STORE>
 __global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_kernel(const __grid_constant__ MergeFrame f,
                                                                                      const __grid_constant__ MergeGeom g,
                                                                                      float *__restrict__ num,
@@ -430,7 +440,7 @@ __global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBL
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (hr_i >= g.Hs || j0 >= g.Ws) return;
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
-    if (HHSR_MERGE_PREFETCH && (threadIdx.x & 1) == 0) {
+    if (HHSR_MERGE_PREFETCH && !STORE && (threadIdx.x & 1) == 0) {
         prefetch_l2(num + base);
         prefetch_l2(den + base);
         prefetch_l2(num + base + 23);
@@ -462,7 +472,7 @@ __global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBL
     }
     // every 3x3 window strictly inside the frame (cj is non-decreasing in p) and a green-is-1 Bayer pattern?
     if (!(ci >= 1 && ci <= g.H - 2 && cj[0] >= 1 && cj[3] <= W - 2 && g.cfa.bayer && g.cfa.dup == 1)) {
-        accumulate_thread_border<ISO>(&f, &g, num, den, hr_i, j0);
+        accumulate_thread_border<ISO, STORE>(&f, &g, num, den, hr_i, j0);
         return;
     }
     // RGGB phase of the pattern: (py0, px0) = position of channel 0 ... pattern(y, x) = RGGB(y + py0, x + px0)
@@ -502,9 +512,9 @@ __global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBL
         if (HHSR_MERGE_RMW_END ? (p == 3) : (p >= 1))
 #pragma unroll
         for (int q = (HHSR_MERGE_RMW_END ? 0 : p - 1); q <= p - 1; ++q) {   // float4 number q of the 12-float slice is complete
-            rmw4(num + base + 4 * q, rr[(4 * q) / 3], n[4 * q], rr[(4 * q + 1) / 3], n[4 * q + 1], rr[(4 * q + 2) / 3],
+            rmw4<STORE>(num + base + 4 * q, rr[(4 * q) / 3], n[4 * q], rr[(4 * q + 1) / 3], n[4 * q + 1], rr[(4 * q + 2) / 3],
                  n[4 * q + 2], rr[(4 * q + 3) / 3], n[4 * q + 3]);
-            rmw4(den + base + 4 * q, rr[(4 * q) / 3], d[4 * q], rr[(4 * q + 1) / 3], d[4 * q + 1], rr[(4 * q + 2) / 3],
+            rmw4<STORE>(den + base + 4 * q, rr[(4 * q) / 3], d[4 * q], rr[(4 * q + 1) / 3], d[4 * q + 1], rr[(4 * q + 2) / 3],
                  d[4 * q + 2], rr[(4 * q + 3) / 3], d[4 * q + 3]);
         }
     }
@@ -811,14 +821,14 @@ static int check_merge_args(const void *raw, const void *num, const void *den, i
     return 0;
 }
 
-template <int VEC>
+template <int VEC, bool STORE>
 static void launch_accumulate_vec(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso, dim3 grid,
                                   dim3 block, cudaStream_t st) {
     if (b.K == 1) {
         if (iso)
-            accumulate_kernel<true, VEC><<<grid, block, 0, st>>>(b.f[0], g, num, den);
+            accumulate_kernel<true, VEC, STORE><<<grid, block, 0, st>>>(b.f[0], g, num, den);
         else
-            accumulate_kernel<false, VEC><<<grid, block, 0, st>>>(b.f[0], g, num, den);
+            accumulate_kernel<false, VEC, STORE><<<grid, block, 0, st>>>(b.f[0], g, num, den);
     } else {
         if (iso)
             accumulate_batch_kernel<true, VEC><<<grid, block, 0, st>>>(b, g, num, den);
@@ -837,15 +847,16 @@ static int pow2_fast_shift(const MergeGeom &g) {
     return -1;
 }
 
-template <int K>
+template <int K, bool STORE>
 static void launch_pow2(const MergeFrame &f, const MergeGeom &g, float *num, float *den, int iso, dim3 grid, dim3 block,
                         cudaStream_t st) {
     if (iso)
-        accumulate_pow2_kernel<true, K><<<grid, block, 0, st>>>(f, g, num, den);
+        accumulate_pow2_kernel<true, K, STORE><<<grid, block, 0, st>>>(f, g, num, den);
     else
-        accumulate_pow2_kernel<false, K><<<grid, block, 0, st>>>(f, g, num, den);
+        accumulate_pow2_kernel<false, K, STORE><<<grid, block, 0, st>>>(f, g, num, den);
 }
 
+template <bool STORE>
 static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso,
                              cudaStream_t st) {
     dim3 block(32, 8);
@@ -853,15 +864,15 @@ static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num
     if (k >= 0) {
         block = dim3(32, HHSR_MERGE_BLOCK_Y);
         dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, HHSR_MERGE_BLOCK_Y));
-        if (k == 0) launch_pow2<0>(b.f[0], g, num, den, iso, grid, block, st);
-        if (k == 1) launch_pow2<1>(b.f[0], g, num, den, iso, grid, block, st);
-        if (k == 2) launch_pow2<2>(b.f[0], g, num, den, iso, grid, block, st);
+        if (k == 0) launch_pow2<0, STORE>(b.f[0], g, num, den, iso, grid, block, st);
+        if (k == 1) launch_pow2<1, STORE>(b.f[0], g, num, den, iso, grid, block, st);
+        if (k == 2) launch_pow2<2, STORE>(b.f[0], g, num, den, iso, grid, block, st);
         return launch_status("merge_accumulate");
     }
     if (g.Ws % 4 == 0)
-        launch_accumulate_vec<4>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8)), block, st);
+        launch_accumulate_vec<4, STORE>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8)), block, st);
     else
-        launch_accumulate_vec<1>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32), ceil_div(g.Hs, 8)), block, st);
+        launch_accumulate_vec<1, STORE>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32), ceil_div(g.Hs, 8)), block, st);
     return launch_status("merge_accumulate");
 }
 
@@ -869,10 +880,9 @@ static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num
 
 using namespace hhsr;
 
-extern "C" int hhsr_merge_accumulate_batch(const float *const *raws, const float *const *flows,
-                                           const float *const *covs, const float *const *rs, int K, int H, int W,
-                                           int ny, int nx, int ts, float *num, float *den, int Hs, int Ws,
-                                           double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
+static int merge_frames(const float *const *raws, const float *const *flows, const float *const *covs, const float *const *rs,
+                        int K, int H, int W, int ny, int nx, int ts, float *num, float *den, int Hs, int Ws, double scale,
+                        const int *cfa_host, int iso, bool store, hhsr_stream_t stream) {
     HHSR_REQUIRE(raws && flows && rs && K > 0, "null frame list");
     HHSR_REQUIRE(iso || covs, "covs required for the steerable kernel");
     if (int e = check_merge_args(raws[0], num, den, H, W, Hs, Ws, scale, cfa_host)) return e;
@@ -886,16 +896,30 @@ extern "C" int hhsr_merge_accumulate_batch(const float *const *raws, const float
             HHSR_REQUIRE(iso || ((uintptr_t)covs[k0 + k] % 16 == 0 && covs[k0 + k]), "covs must be 16-byte aligned");
             b.f[k] = MergeFrame{raws[k0 + k], flows[k0 + k], iso ? nullptr : covs[k0 + k], rs[k0 + k]};
         }
-        if (int e = launch_accumulate(b, g, num, den, iso, (cudaStream_t)stream)) return e;
+        const int e = store ? launch_accumulate<true>(b, g, num, den, iso, (cudaStream_t)stream)
+                            : launch_accumulate<false>(b, g, num, den, iso, (cudaStream_t)stream);
+        if (e) return e;
     }
     return 0;
+}
+
+extern "C" int hhsr_merge_accumulate_batch(const float *const *raws, const float *const *flows,
+                                           const float *const *covs, const float *const *rs, int K, int H, int W,
+                                           int ny, int nx, int ts, float *num, float *den, int Hs, int Ws,
+                                           double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
+    return merge_frames(raws, flows, covs, rs, K, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, false, stream);
 }
 
 extern "C" int hhsr_merge_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
                                      const float *covs, const float *r, float *num, float *den, int Hs, int Ws,
                                      double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
-    return hhsr_merge_accumulate_batch(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale,
-                                       cfa_host, iso, stream);
+    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, false, stream);
+}
+
+extern "C" int hhsr_merge_init_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
+                                          const float *covs, const float *r, float *num, float *den, int Hs, int Ws,
+                                          double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
+    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, true, stream);
 }
 
 static int launch_merge_ref(const float *raw, const float *covs, const MergeGeom &g, float *num, float *den, int iso,

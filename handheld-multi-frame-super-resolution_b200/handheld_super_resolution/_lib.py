@@ -37,6 +37,7 @@ SIGNATURES = {
     "hhsr_robustness": [_P, _P, _P, _I, _I, _P, _I, _I, _I, _D, _D, _D, _D, _P, _P],
     "hhsr_local_min5": [_P, _I, _I, _P, _P, _P],
     "hhsr_merge_accumulate": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _D, _IP, _I, _P],
+    "hhsr_merge_init_accumulate": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _D, _IP, _I, _P],
     "hhsr_merge_accumulate_batch": [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _I,
                                     _I, _P, _P, _I, _I, _D, _IP, _I, _P],
     "hhsr_merge_ref": [_P, _I, _I, _P, _P, _P, _I, _I, _D, _IP, _I, _P, _I, _I, _D, _I, _I, _I, _P],

@@ -13,8 +13,10 @@ def _check_acc(num, den):
     assert num.dtype == torch.float32 and den.dtype == torch.float32
 
 
-def merge(comp_img, alignments, covs, r, num, den, cfa_pattern, config):
-    """Accumulate comp frame J_n into num/den with its flow, covariances and robustness (merge.py:236-288)."""
+def merge(comp_img, alignments, covs, r, num, den, cfa_pattern, config, init=False):
+    """Accumulate comp frame J_n into num/den with its flow, covariances and robustness (merge.py:236-288).
+    init=True (B200 addition): num/den are initialised with this frame's contribution — equal to accumulating into
+    zero-filled arrays, without needing them zero-filled (main() does this for the first comp frame)."""
     if config.mode != "bayer":
         raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
     _check_acc(num, den)
@@ -22,7 +24,7 @@ def merge(comp_img, alignments, covs, r, num, den, cfa_pattern, config):
     H, W = comp_img.shape
     iso = config.merging.kernel == "iso"
     ny, nx, _ = alignments.shape
-    _lib.call("hhsr_merge_accumulate", _lib.ptr(comp_img), H, W, _lib.ptr(alignments), ny, nx,
+    _lib.call("hhsr_merge_init_accumulate" if init else "hhsr_merge_accumulate", _lib.ptr(comp_img), H, W, _lib.ptr(alignments), ny, nx,
               int(config.block_matching.tuning.tile_size), _lib.ptr(None if iso else covs), _lib.ptr(r), _lib.ptr(num),
               _lib.ptr(den), num.shape[0], num.shape[1], float(config.scale), _lib.cfa_array(cfa_pattern), int(iso),
               _lib.stream())

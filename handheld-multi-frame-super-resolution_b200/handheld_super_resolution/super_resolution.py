@@ -180,18 +180,22 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     H, W = cuda_ref_img.shape
     scale = config.scale
     output_size = (round(scale * H), round(scale * W))
+    n_images = len(comp_imgs)
+    ids = list(range(n_images) if frame_ids is None else frame_ids)
+    # the first comp frame initialises the accumulators (merge(init=True)); only a burst/shard without comp frames
+    # needs them zero-filled (the reference uploads host zeros, super_resolution.py:123-124)
     if accumulators is not None:
         num, den = accumulators
         assert tuple(num.shape) == (*output_size, 3) and tuple(den.shape) == (*output_size, 3)
-        num.zero_(), den.zero_()
+        if not ids:
+            num.zero_(), den.zero_()
     else:
-        num = torch.zeros((*output_size, 3), dtype=torch.float32, device=dev)
-        den = torch.zeros((*output_size, 3), dtype=torch.float32, device=dev)
+        alloc = torch.empty if ids else torch.zeros
+        num = alloc((*output_size, 3), dtype=torch.float32, device=dev)
+        den = alloc((*output_size, 3), dtype=torch.float32, device=dev)
     accumulated_r = torch.zeros((H, W), dtype=torch.float64, device=dev) if accumulate_r else None
 
     _mark("ref_side")
-    n_images = len(comp_imgs)
-    ids = list(range(n_images) if frame_ids is None else frame_ids)
     feed = FrameFeeder(comp_imgs, ids, config, dev)
     r_maps = []
     main_stream = torch.cuda.current_stream(dev)
@@ -229,7 +233,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
         if accumulate_r:
             r_maps.append(r)      # accumulated_r += r (super_resolution.py:159), summed in frame order after the loop
         covs = estimate_kernels_(cuda_img, config)
-        merge_(cuda_img, flow, covs, r, num, den, cfa_pattern, config)
+        merge_(cuda_img, flow, covs, r, num, den, cfa_pattern, config, init=(k == 0))
         feed.release(k)
         if debug_mode:
             debug_dict["robustness"].append(r.cpu().numpy())

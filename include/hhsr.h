@@ -131,6 +131,11 @@ int hhsr_normalize_raw_u16(const unsigned short *raw, int H, int W, const float 
 int hhsr_merge_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
                           const float *covs, const float *r, float *num, float *den, int Hs, int Ws, double scale,
                           const int *cfa_host, int iso, hhsr_stream_t stream);
+/* same arguments; num/den are INITIALISED with this frame's contribution instead of being updated (their previous
+ * contents are ignored): the first comp frame of a burst needs no zero-filled accumulators (B200 addition). */
+int hhsr_merge_init_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
+                               const float *covs, const float *r, float *num, float *den, int Hs, int Ws,
+                               double scale, const int *cfa_host, int iso, hhsr_stream_t stream);
 /* Same arithmetic for K comp frames in one pass over the accumulators (frame order preserved per pixel).
  * raws/flows/covs/rs: HOST arrays of K device pointers. */
 int hhsr_merge_accumulate_batch(const float *const *raws, const float *const *flows, const float *const *covs,

@@ -483,6 +483,22 @@ def test_main_uint16_burst_equals_float_burst():
         assert torch.equal(torch.nan_to_num(out_f), torch.nan_to_num(o))
 
 
+@pytest.mark.parametrize("scale", [2, 1.5])
+def test_merge_init_equals_accumulate_into_zeros(stage, scale):
+    """merge(init=True) on garbage-filled accumulators == merge() on zero-filled ones, bit for bit (fast path and
+    generic kernel)."""
+    from handheld_super_resolution import merge as MG
+    cfg = attr_cfg(scale=scale)
+    H, W = stage["raw"].shape
+    shape = (round(scale * H), round(scale * W), 3)
+    args = (dev(stage["raw"]), dev(stage["flow_irreg"]), dev(stage["covs1"]), dev(stage["r_rand"]))
+    n0, d0 = torch.zeros(shape, device="cuda"), torch.zeros(shape, device="cuda")
+    MG.merge(*args, n0, d0, CFA, cfg)
+    n1, d1 = torch.full(shape, float("nan"), device="cuda"), torch.full(shape, 123.0, device="cuda")
+    MG.merge(*args, n1, d1, CFA, cfg, init=True)
+    assert torch.equal(n0, n1) and torch.equal(d0, d1)
+
+
 def test_divide_and_add():
     from handheld_super_resolution.utils import add, divide
     g = torch.Generator(device="cuda").manual_seed(0)
