@@ -141,7 +141,25 @@ def timed_main(SR, burst, cfg, label):
     return out, dbg
 
 
+def install_copysign_shim():
+    """numba 0.65 + NVVM 12.9 reject libdevice's __nv_copysign ("Unsupported intrinsic: llvm.copysign.f64"): exact
+    bit-twiddling lowering of math.copysign(f64, f64) instead (same shim as tests/golden/make_golden_gpu.py)."""
+    import math
+    from llvmlite import ir
+    from numba import types
+    from numba.cuda.mathimpl import lower
+
+    @lower(math.copysign, types.float64, types.float64)
+    def copysign_f64(context, builder, sig, args):
+        i64 = ir.IntType(64)
+        xi, yi = builder.bitcast(args[0], i64), builder.bitcast(args[1], i64)
+        mag = builder.and_(xi, ir.Constant(i64, 0x7FFFFFFFFFFFFFFF))
+        sgn = builder.and_(yi, ir.Constant(i64, 0x8000000000000000))
+        return builder.bitcast(builder.or_(mag, sgn), ir.DoubleType())
+
+
 def main():
+    install_copysign_shim()
     n, H, W, scale, Ts = 8, 3000, 4000, 2, 32
     if len(sys.argv) > 5:
         n, H, W, scale, Ts = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4]), int(sys.argv[5])

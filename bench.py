@@ -156,7 +156,7 @@ def run_reference_arm(args, wl, wl_name):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_frames, crop = 4, 704
+    n_frames, crop = max(2, min(wl["n"], cores + 1)), 704       # one comp frame per host core (up to the whole burst)
     burst, cfg, scaling = cpu_sample(wl, n_frames, crop, cores)
     nproc = min(cores, n_frames - 1)
     pool = mp.get_context("fork").Pool(nproc) if nproc > 1 else None
@@ -309,12 +309,16 @@ def run_cuda_arm(args, wl, wl_name):
     launches = (_lib.launch_count - launches0)
     merge_ms = [a.elapsed_time(b) for a, b in merge_events]
     merge_events.clear()
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, _, t2 = timed(step_e2e, args.steps)
-    ms_lat, _, t2 = timed(lambda: step_e2e(pipelined=False), max(2, args.steps // 2))   # one burst at a time, host-synchronous
-    step_e2e(u16=True)
-    ms_u16, _, t2 = timed(lambda: step_e2e(u16=True), args.steps)
+    if args.no_e2e:        # profiling runs (ncu replays every launch): the resident step only
+        ms_e2e = ms_lat = ms_u16 = float("nan")
+        t2 = t1
+    else:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, _, t2 = timed(step_e2e, args.steps)
+        ms_lat, _, t2 = timed(lambda: step_e2e(pipelined=False), max(2, args.steps // 2))   # one burst at a time, host-synchronous
+        step_e2e(u16=True)
+        ms_u16, _, t2 = timed(lambda: step_e2e(u16=True), args.steps)
     clocks = sampler.stop(t0, t2) if rank == 0 else None
     SR.merge = orig_merge
 
@@ -380,6 +384,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="20x12MP_s2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer legs (e2e fields are NaN)")
     ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "reduce_scatter", "allreduce"],
                     help="N > 1: how the frame-sharded accumulators are summed (auto = p2p when available)")
     args = ap.parse_args()
