@@ -103,74 +103,6 @@ __global__ void __launch_bounds__(DBX *DBY) gauss_downsample_kernel(const float 
     dst[(size_t)oy * w2 + ox] = acc;
 }
 
-// Factor 2 (radius 4), the level that reads the full-resolution grey image: CTA = 32 x 32 kept outputs (input tile
-// 72 x 72, 1.27x halo instead of 1.69x for 32 x 8), register-tiled passes: in the y pass a thread owns one tile column
-// and 8 consecutive output rows (23 shared-memory reads feed 72 FMAs), in the x pass 4 consecutive outputs of a row
-// (15 reads feed 36 FMAs).  Taps are accumulated in the same order as gauss_downsample_kernel<2, 4> (bit-equal).
-constexpr int D2T = 32, D2W = D2T * 2 + 8;   // outputs per CTA side, input tile side
-__global__ void __launch_bounds__(256) gauss_downsample2_kernel(const float *__restrict__ src, int h, int w, Taps taps,
-                                                                float *__restrict__ dst, int h2, int w2) {
-    __shared__ __align__(16) float tin[D2W * D2W];
-    __shared__ float tmp[D2T * D2W];
-    const int ox0 = blockIdx.x * D2T, oy0 = blockIdx.y * D2T;
-    const int ix0 = ox0 * 2, iy0 = oy0 * 2;
-    const int tid = threadIdx.x;
-    const bool vec = (w % 4 == 0) && (((uintptr_t)src) % 16 == 0);
-    if (vec) {      // 72 floats = 18 float4 per tile row (ix0 is a multiple of 64)
-        for (int t = tid; t < D2W * (D2W / 4); t += 256) {
-            const int ly = t / (D2W / 4), l4 = t - ly * (D2W / 4);
-            const int gy = iy0 + ly, gx = ix0 + 4 * l4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gy < h && gx + 3 < w) {
-                v = __ldg(reinterpret_cast<const float4 *>(src + (size_t)gy * w + gx));
-            } else if (gy < h) {
-                const float *q = src + (size_t)gy * w;
-                v.x = gx < w ? __ldg(q + gx) : 0.f, v.y = gx + 1 < w ? __ldg(q + gx + 1) : 0.f;
-                v.z = gx + 2 < w ? __ldg(q + gx + 2) : 0.f, v.w = gx + 3 < w ? __ldg(q + gx + 3) : 0.f;
-            }
-            *reinterpret_cast<float4 *>(tin + ly * D2W + 4 * l4) = v;
-        }
-    } else {
-        for (int t = tid; t < D2W * D2W; t += 256) {
-            const int ly = t / D2W, lx = t - ly * D2W;
-            const int gy = iy0 + ly, gx = ix0 + lx;
-            tin[t] = (gy < h && gx < w) ? __ldg(src + (size_t)gy * w + gx) : 0.f;
-        }
-    }
-    __syncthreads();
-    // y pass: work item = (column c, group of 8 output rows)
-    for (int it = tid; it < D2W * 4; it += 256) {
-        const int c = it % D2W, r0 = (it / D2W) * 8;
-        float in[23];
-#pragma unroll
-        for (int k = 0; k < 23; ++k) in[k] = tin[(2 * r0 + k) * D2W + c];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            float acc = 0.f;
-#pragma unroll
-            for (int a = 0; a < 9; ++a) acc = fmaf(taps.g[a], in[2 * r + a], acc);
-            tmp[(r0 + r) * D2W + c] = acc;
-        }
-    }
-    __syncthreads();
-    // x pass: thread = 4 consecutive outputs of one row
-    const int r = tid >> 3, x0 = (tid & 7) * 4;
-    const int oy = oy0 + r;
-    if (oy >= h2) return;
-    float in[15];
-#pragma unroll
-    for (int k = 0; k < 15; ++k) in[k] = tmp[r * D2W + 2 * x0 + k];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ox = ox0 + x0 + j;
-        if (ox >= w2) break;
-        float acc = 0.f;
-#pragma unroll
-        for (int b = 0; b < 9; ++b) acc = fmaf(taps.g[b], in[2 * j + b], acc);
-        dst[(size_t)oy * w2 + ox] = acc;
-    }
-}
-
 }  // namespace hhsr
 
 using namespace hhsr;
@@ -213,8 +145,7 @@ extern "C" int hhsr_gauss_downsample(const float *src, int h, int w, int factor,
     dim3 block(DBX, DBY), grid(ceil_div(w2, DBX), ceil_div(h2, DBY));
     cudaStream_t st = (cudaStream_t)stream;
     if (factor == 2 && radius == 4) {
-        dim3 g2(ceil_div(w2, D2T), ceil_div(h2, D2T));
-        gauss_downsample2_kernel<<<g2, 256, 0, st>>>(src, h, w, t, dst, h2, w2);
+        gauss_downsample_kernel<2, 4><<<grid, block, smem, st>>>(src, h, w, factor, radius, t, dst, h2, w2);
     } else if (factor == 4 && radius == 8) {
         gauss_downsample_kernel<4, 8><<<grid, block, smem, st>>>(src, h, w, factor, radius, t, dst, h2, w2);
     } else {
