@@ -72,14 +72,30 @@ class FrameFeeder:
     compute stream; uint16 frames (sensor counts) cross PCIe as 2 bytes per pixel and are normalised on the device
     (utils_dng.RawNormalization, the reference's utils_dng.py:146-160).  CUDA float32 frames pass through."""
     SLOTS = 3
+    _RINGS = {}     # (device, compute stream, role, shape, dtype, slot) -> [buffer, event "slot free"]: staging buffers live
+                    # across bursts, so the first uploads of burst i+1 need not wait for the compute stream to drain burst i
 
-    def __init__(self, frames, ids, config, device):
-        self.frames, self.ids, self.config, self.device = frames, list(ids), config, device
+    def __init__(self, frames, ids, config, device, role="comp"):
+        self.frames, self.ids, self.config, self.device, self.role = frames, list(ids), config, device, role
         self.compute = torch.cuda.current_stream(device)
         self.copy = _copy_stream(device)
         self.norm = None
-        self.ring, self.free_ev, self.ready = {}, {}, {}
-        self.next_k = 0
+        self.ready = {}
+
+    def _slot(self, host, k):
+        key = (self.device.index, self.compute.cuda_stream, self.role, tuple(host.shape), host.dtype, k % self.SLOTS)
+        slot = FrameFeeder._RINGS.get(key)
+        if slot is None:
+            buf = torch.empty(host.shape, dtype=host.dtype, device=self.device)   # compute-stream pool
+            ev = torch.cuda.Event()
+            ev.record(self.compute)        # the block may still be in use by earlier work of the compute stream
+            if len(FrameFeeder._RINGS) > 64:      # shapes changed many times: drop the old staging buffers
+                FrameFeeder._RINGS.clear()
+            slot = FrameFeeder._RINGS[key] = [buf, ev]
+        return slot
+
+    def owns(self, t):
+        return any(t is s[0] for s in FrameFeeder._RINGS.values())
 
     def _stage(self, k):
         """Enqueue the H2D copy of the k-th frame of `ids` (no-op for device frames)."""
@@ -90,19 +106,14 @@ class FrameFeeder:
             self.ready[k] = (frame, None)
             return
         host = _host_tensor(frame)
-        key = (host.dtype, k % self.SLOTS)
-        if key not in self.ring:
-            self.ring[key] = torch.empty(host.shape, dtype=host.dtype, device=self.device)   # compute-stream pool
-            ev = torch.cuda.Event()
-            ev.record(self.compute)        # the block may still be in use by earlier work of the compute stream
-            self.free_ev[key] = ev
-        buf = self.ring[key]
+        slot = self._slot(host, k)
+        buf = slot[0]
         with torch.cuda.stream(self.copy):
-            self.copy.wait_event(self.free_ev[key])       # previous user of this slot is done
+            self.copy.wait_event(slot[1])                 # previous user of this slot is done
             buf.copy_(host, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy)
-        self.ready[k] = (buf, ev, key)
+        self.ready[k] = (buf, ev, slot)
 
     def get(self, k):
         """k-th frame as float32 on the compute stream; prefetches frame k + 1.  Call release(k) after its last use."""
@@ -128,7 +139,7 @@ class FrameFeeder:
         if item is not None and item[1] is not None:
             ev = torch.cuda.Event()
             ev.record(self.compute)
-            self.free_ev[item[2]] = ev
+            item[2][1] = ev
 
 
 def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulators=None, finalize_fn=None):
@@ -161,9 +172,9 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     t1 = time.perf_counter()
 
     _mark("start")
-    ref_feed = FrameFeeder([ref_img], [0], config, dev)
+    ref_feed = FrameFeeder([ref_img], [0], config, dev, role="ref")
     cuda_ref_img = ref_feed.get(0)
-    if any(cuda_ref_img is b for b in ref_feed.ring.values()):
+    if ref_feed.owns(cuda_ref_img):
         cuda_ref_img = cuda_ref_img.clone()      # the reference frame outlives its staging slot
     ref_feed.release(0)
     cfa_pattern = config.exif.cfa_pattern

@@ -499,6 +499,35 @@ def test_merge_init_equals_accumulate_into_zeros(stage, scale):
     assert torch.equal(n0, n1) and torch.equal(d0, d1)
 
 
+def test_process_on_burst_archives(tmp_path):
+    """process() (super_resolution.py:203-360 minus DNG I/O and the CPU ISP): a float32 archive and the same burst as
+    uint16 sensor counts give the same image; the config is enriched like the reference does (exif, noise curves,
+    SNR-derived parameters)."""
+    import hhsr_oracle as O
+    from handheld_super_resolution import process
+    from handheld_super_resolution.config import load_config
+    from handheld_super_resolution.synthetic import ALPHA_ISO100, BETA_ISO100, synth_burst
+    burst, _ = synth_burst(3, 704, 736, seed=21, max_shift=2.0, quantize_bits=12)
+    black, white, wb = [64, 64, 64, 64], 4095, [1.0, 1.0, 1.0, 0.0]
+    counts = np.round(burst * (white - 64) + 64).astype(np.uint16)
+    fburst = O.normalize_raw(counts, CFA, black, white, wb)
+    std, diff = curves()
+    common = dict(cfa_pattern=np.asarray(CFA), white_balance=np.asarray(wb), alpha=ALPHA_ISO100, beta=BETA_ISO100,
+                  std_curve=std, diff_curve=diff)
+    np.savez(tmp_path / "f32.npz", burst=fburst, **common)
+    np.savez(tmp_path / "u16.npz", burst=counts, black_levels=np.asarray(black), white_level=white, **common)
+    outs = []
+    for name in ("f32.npz", "u16.npz"):
+        cfg = load_config(overrides={"scale": 2, "block_matching": {"tuning": {"tile_size": 32}}})
+        img, dbg = process(str(tmp_path / name), cfg)
+        assert img.shape == (1408, 1472, 3) and img.dtype == np.float32
+        assert cfg.exif.cfa_pattern == CFA and len(cfg.noise_model.std_curve) == 1001
+        assert cfg.block_matching.tuning.tile_sizes[0] == 32 and "k_detail" in cfg.merging.tuning
+        outs.append(img)
+    assert np.array_equal(np.nan_to_num(outs[0]), np.nan_to_num(outs[1]))
+    assert np.isfinite(outs[0]).mean() > 0.999 and 0.05 < np.nanmean(outs[0]) < 0.95
+
+
 def test_divide_and_add():
     from handheld_super_resolution.utils import add, divide
     g = torch.Generator(device="cuda").manual_seed(0)
