@@ -205,20 +205,34 @@ struct CovQuads {
     float4 tr, tl, br, bl;
 };
 
-// bilinear blend of the four covariance quads (x first, then y; merge.py:365-389) and its pre-scaled inverse
-__device__ __forceinline__ void cov_form(const float4 &tr, const float4 &tl, const float4 &br, const float4 &bl, float frx,
-                                         float fry, float &qxx, float &qxy, float &qyy) {
+// Bilinear blend of the four covariance quads (merge.py:365-389) and its pre-scaled inverse.  The blend runs along y
+// first (the two quad COLUMNS), then along x: the fast path shares the y-blended columns between the four pixels of a
+// thread, and every kernel uses this order so that they stay bit-equal (the reference blends x first in float64;
+// the difference is float32 rounding).
+struct CovCol {
+    float xx, xy, yy;
+};
+__device__ __forceinline__ CovCol cov_column(const float4 &top, const float4 &bot, float fry) {
+    CovCol c;
+    c.xx = fmaf(fry, bot.x - top.x, top.x);
+    c.xy = fmaf(fry, bot.y - top.y, top.y);
+    c.yy = fmaf(fry, bot.w - top.w, top.w);
+    return c;
+}
+__device__ __forceinline__ void cov_form_cols(const CovCol &l, const CovCol &r, float frx, float &qxx, float &qxy, float &qyy) {
     const float kS = -0.72134752044448170368f;   // -0.5 * log2(e)
-    const float top_xx = fmaf(frx, tl.x - tr.x, tr.x), bot_xx = fmaf(frx, bl.x - br.x, br.x);
-    const float top_xy = fmaf(frx, tl.y - tr.y, tr.y), bot_xy = fmaf(frx, bl.y - br.y, br.y);
-    const float top_yy = fmaf(frx, tl.w - tr.w, tr.w), bot_yy = fmaf(frx, bl.w - br.w, br.w);
-    const float cxx = fmaf(fry, bot_xx - top_xx, top_xx);
-    const float cxy = fmaf(fry, bot_xy - top_xy, top_xy);
-    const float cyy = fmaf(fry, bot_yy - top_yy, top_yy);
+    const float cxx = fmaf(frx, r.xx - l.xx, l.xx);
+    const float cxy = fmaf(frx, r.xy - l.xy, l.xy);
+    const float cyy = fmaf(frx, r.yy - l.yy, l.yy);
     const float inv_det = __fdividef(kS, fmaf(cxx, cyy, -(cxy * cxy)));      // merge.py:391-396
     qxx = inv_det * cyy;
     qxy = -2.0f * inv_det * cxy;
     qyy = inv_det * cxx;
+}
+// tr/br: quads at column fx0 (rows fy0 / cy1), tl/bl: at column cx1
+__device__ __forceinline__ void cov_form(const float4 &tr, const float4 &tl, const float4 &br, const float4 &bl, float frx,
+                                         float fry, float &qxx, float &qxy, float &qyy) {
+    cov_form_cols(cov_column(tr, br, fry), cov_column(tl, bl, fry), frx, qxx, qxy, qyy);
 }
 
 template <bool ISO>
@@ -485,7 +499,20 @@ __global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBL
     // fraction t/2 (+ 1/2 for even c) — cov_coord() without its border cases
     const int oqy = ((ci - 1) >> 1) * cw;
     const float fry = fmaf(0.5f, ty, (ci & 1) ? 0.0f : 0.5f);
-    const float4 *c4 = reinterpret_cast<const float4 *>(f.covs);
+    // the four pixels span at most 3 (K = 0: 4) LR pixels, i.e. quad columns i0 .. i0 + NCOL - 1: blend them along y once
+    // (2 NCOL loads instead of 16) and pick the column pair of each pixel
+    constexpr int NCOL = (K == 0) ? 4 : 3;
+    CovCol col[NCOL];
+    const int i0 = (cj[0] - 1) >> 1;
+    if (!ISO) {
+        const float4 *q0 = reinterpret_cast<const float4 *>(f.covs) + (oqy + i0);
+        const float4 *q1 = q0 + cw;
+        const int dmax = ((cj[3] - 1) >> 1) - i0;             // column dmax + 1 is the last one any pixel needs (it exists)
+        col[0] = cov_column(__ldg(q0), __ldg(q1), fry);
+        col[1] = cov_column(__ldg(q0 + 1), __ldg(q1 + 1), fry);
+#pragma unroll
+        for (int c = 2; c < NCOL; ++c) col[c] = (c <= dmax + 1) ? cov_column(__ldg(q0 + c), __ldg(q1 + c), fry) : col[c - 1];
+    }
     float n[12], d[12], rr[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -494,11 +521,13 @@ __global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBL
         if (ISO) {
             qxx = qyy = 2.0f * -0.72134752044448170368f, qxy = 0.0f;
         } else {
-            const float4 *q0 = c4 + (oqy + ((cj[p] - 1) >> 1));
-            const float4 *q1 = c4 + (oqy + cw + ((cj[p] - 1) >> 1));
+            const int dcol = ((cj[p] - 1) >> 1) - i0;         // this pixel blends columns (dcol, dcol + 1)
             const float frx = fmaf(0.5f, tx[p], (cj[p] & 1) ? 0.0f : 0.5f);
-            const float4 tr = __ldg(q0), tl = __ldg(q0 + 1), br = __ldg(q1), bl = __ldg(q1 + 1);
-            cov_form(tr, tl, br, bl, frx, fry, qxx, qxy, qyy);
+            CovCol l = col[0], r = col[1];
+#pragma unroll
+            for (int c = 1; c < NCOL - 1; ++c)
+                if (dcol == c) l = col[c], r = col[c + 1];
+            cov_form_cols(l, r, frx, qxx, qxy, qyy);
         }
         float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, a[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
         merge_taps_off(f.raw, W, orow + cj[p], tx[p], ty, qxx, qxy, qyy, v, a);
