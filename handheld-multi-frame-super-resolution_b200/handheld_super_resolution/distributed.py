@@ -88,8 +88,17 @@ class P2PReduce:
         return cls._cache[key]
 
     def rows(self):
+        """Row slice of this rank.  Rank 0 also RECEIVES every other rank's finished slice (half the bytes of the
+        num + den it would otherwise pull), so it takes a slice half as tall: inbound NVLink bytes are then equal on
+        all ranks ((G-1)(a S + b S/2) = (G-1) b S  =>  a = b/2)."""
         Hs = self.shape[0]
-        return (self.rank * Hs) // self.world, ((self.rank + 1) * Hs) // self.world
+        w = [0.5] + [1.0] * (self.world - 1)
+        tot = sum(w)
+        edge = [0]
+        for x in w:
+            edge.append(edge[-1] + x)
+        lo, hi = round(edge[self.rank] / tot * Hs), round(edge[self.rank + 1] / tot * Hs)
+        return lo, (Hs if self.rank == self.world - 1 else hi)
 
     def finalize(self, ref_img, covs, num, den, acc_rob, cfa_pattern, config):
         import ctypes as C
