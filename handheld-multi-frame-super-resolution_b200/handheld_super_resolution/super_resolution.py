@@ -40,13 +40,16 @@ def _copy_stream(device):
 _ALIGN_STREAMS = {}
 
 
-def _align_stream(device):
-    """Persistent high-priority side stream on which the alignment chain of frame k+1 (grey image, pyramid, block
-    matching, ICA: many small latency-bound launches) runs while the main stream weights and merges frame k."""
-    s = _ALIGN_STREAMS.get(device.index)
+def _align_stream(device, i=0):
+    """Persistent high-priority side streams on which the alignment chains of the next frames (grey image, pyramid,
+    block matching, ICA: many small latency-bound launches) run while the main stream weights and merges frame k."""
+    s = _ALIGN_STREAMS.get((device.index, i))
     if s is None:
-        s = _ALIGN_STREAMS[device.index] = torch.cuda.Stream(device=device, priority=-1)
+        s = _ALIGN_STREAMS[(device.index, i)] = torch.cuda.Stream(device=device, priority=-1)
     return s
+
+
+ALIGN_AHEAD = int(os.environ.get("HHSR_ALIGN_AHEAD", "1"))   # alignment chains in flight ahead of the merge (0: one stream)
 
 
 def _host_tensor(frame):
@@ -71,7 +74,7 @@ class FrameFeeder:
     compute stream, so the caching allocator serves them from the same pool every burst), one frame ahead of the
     compute stream; uint16 frames (sensor counts) cross PCIe as 2 bytes per pixel and are normalised on the device
     (utils_dng.RawNormalization, the reference's utils_dng.py:146-160).  CUDA float32 frames pass through."""
-    SLOTS = 3
+    SLOTS = 2 + max(ALIGN_AHEAD, 1)      # frame being merged + frames being aligned + frame being uploaded
     _RINGS = {}     # (device, compute stream, role, shape, dtype, slot) -> [buffer, event "slot free"]: staging buffers live
                     # across bursts, so the first uploads of burst i+1 need not wait for the compute stream to drain burst i
 
@@ -210,16 +213,16 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     feed = FrameFeeder(comp_imgs, ids, config, dev)
     r_maps = []
     main_stream = torch.cuda.current_stream(dev)
-    two_streams = os.environ.get("HHSR_SINGLE_STREAM", "0") != "1" and not verbose_2
-    align_stream = _align_stream(dev) if two_streams else main_stream
+    ahead = 0 if (os.environ.get("HHSR_SINGLE_STREAM", "0") == "1" or verbose_2) else ALIGN_AHEAD
 
     def start_alignment(k):
-        """Frame k: H2D wait (+ uint16 normalisation) on the main stream, then grey image and alignment on the
-        alignment stream.  Returns (frame, flow, event marking the flow ready)."""
-        cuda_img = feed.get(k)          # H2D of frame k+1 overlaps the work on frame k
-        if not two_streams:
+        """Frame k: H2D wait (+ uint16 normalisation) on the main stream, then grey image and alignment on one of the
+        alignment streams.  Returns (frame, flow, event marking the flow ready)."""
+        cuda_img = feed.get(k)          # H2D of frame k+1 overlaps the work on the earlier frames
+        if ahead == 0:
             grey = compute_grey_images(cuda_img, grey_method)
             return cuda_img, align_(ref_pyramid, tyled_pyr, ref_tiled_fft, ref_gradx, ref_grady, ref_hessian, grey, config), None
+        align_stream = _align_stream(dev, k % ahead)
         ready = torch.cuda.Event()
         ready.record(main_stream)       # frame (and, the first time, the reference-side products) are ready
         with torch.cuda.stream(align_stream):
@@ -230,10 +233,13 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
             done.record(align_stream)
         return cuda_img, flow, done
 
-    nxt = start_alignment(0) if ids else None
+    from collections import deque
+    depth = max(ahead, 1)
+    inflight = deque(start_alignment(j) for j in range(min(depth, len(ids))))
     for k, im_id in enumerate(ids):
-        cuda_img, flow, done = nxt
-        nxt = start_alignment(k + 1) if k + 1 < len(ids) else None     # overlaps the rest of this iteration
+        cuda_img, flow, done = inflight.popleft()
+        if k + depth < len(ids):
+            inflight.append(start_alignment(k + depth))     # overlaps the rest of this iteration (and the next ones)
         if done is not None:
             main_stream.wait_event(done)
             flow.record_stream(main_stream)
