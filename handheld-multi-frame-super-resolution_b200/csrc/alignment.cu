@@ -337,13 +337,13 @@ __global__ void __launch_bounds__(NT) ica_kernel(const float *__restrict__ ref, 
     if (tid == 0) flow[(size_t)py * nx + px] = make_float2(s_flow[0], s_flow[1]);
 }
 
-// ts = 32 (the default tile size, zero-fill sampling): one thread = 4 consecutive pixels of a tile row, so the
-// bilinear taps of its pixels overlap (2 x 5 moving samples instead of 4 x 4) and ref / gradients load as float4;
+// ts = 32 (the default tile size, zero-fill sampling): one thread = 4 x 2 pixels of a tile (128 threads per tile), so the
+// bilinear taps of its pixels overlap (3 x 5 moving samples instead of 8 x 4) and ref / gradients load as float4;
 // the two block-wide sums of an iteration are finished redundantly by every thread from double-buffered per-warp
 // partials (one barrier per iteration instead of two, no serial solve by thread 0).  Same per-pixel arithmetic as
 // ica_kernel<32, 1, 256>; only the summation order of B differs (float32 rounding level).
 template <bool VEC4>
-__global__ void __launch_bounds__(256) ica32_kernel(const float *__restrict__ ref, const float *__restrict__ gradx,
+__global__ void __launch_bounds__(128) ica32_kernel(const float *__restrict__ ref, const float *__restrict__ gradx,
                                                     const float *__restrict__ grady, int ref_w, const float4 *__restrict__ hessian,
                                                     const float *__restrict__ mov, int h, int w, float2 *__restrict__ flow, int nx,
                                                     int n_iter) {
@@ -354,22 +354,23 @@ __global__ void __launch_bounds__(256) ica32_kernel(const float *__restrict__ re
     const float det = A00 * A11 - A01 * A10;
     if (fabsf(det) < 1e-10f) return;                                            // ICA.py:219-221 (block-uniform)
     const float det_inv = 1.0f / det;
-    __shared__ float s_red[2][2][8];
-    const int lx = (tid & 7) * 4, ly = tid >> 3;
+    __shared__ float s_red[2][2][4];
+    const int lx = (tid & 7) * 4, ly = (tid >> 3) * 2;
     const int gx0 = px * TS + lx, gy0 = py * TS + ly;
-    float rc[4], gx[4], gy[4];
-    {
-        const size_t o = (size_t)gy0 * ref_w + gx0;
+    float rc[2][4], gx[2][4], gy[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const size_t o = (size_t)(gy0 + r) * ref_w + gx0;
         if (VEC4) {
             const float4 a = __ldg(reinterpret_cast<const float4 *>(ref + o));
             const float4 b = __ldg(reinterpret_cast<const float4 *>(gradx + o));
             const float4 c = __ldg(reinterpret_cast<const float4 *>(grady + o));
-            rc[0] = a.x, rc[1] = a.y, rc[2] = a.z, rc[3] = a.w;
-            gx[0] = b.x, gx[1] = b.y, gx[2] = b.z, gx[3] = b.w;
-            gy[0] = c.x, gy[1] = c.y, gy[2] = c.z, gy[3] = c.w;
+            rc[r][0] = a.x, rc[r][1] = a.y, rc[r][2] = a.z, rc[r][3] = a.w;
+            gx[r][0] = b.x, gx[r][1] = b.y, gx[r][2] = b.z, gx[r][3] = b.w;
+            gy[r][0] = c.x, gy[r][1] = c.y, gy[r][2] = c.z, gy[r][3] = c.w;
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) rc[k] = __ldg(ref + o + k), gx[k] = __ldg(gradx + o + k), gy[k] = __ldg(grady + o + k);
+            for (int k = 0; k < 4; ++k) rc[r][k] = __ldg(ref + o + k), gx[r][k] = __ldg(gradx + o + k), gy[r][k] = __ldg(grady + o + k);
         }
     }
     const float2 f0 = flow[(size_t)py * nx + px];
@@ -378,36 +379,42 @@ __global__ void __launch_bounds__(256) ica32_kernel(const float *__restrict__ re
         const int ix = (int)ax, iy = (int)ay;                                   // trunc toward zero
         const float frx = ax - truncf(ax), fry = ay - truncf(ay);              // signed modf
         const int X = gx0 + ix, Y = gy0 + iy;
-        float m0[5], m1[5];
-        if (X >= 0 && X + 4 < w && Y >= 0 && Y + 1 < h) {
+        float m[3][5];
+        if (X >= 0 && X + 4 < w && Y >= 0 && Y + 2 < h) {
             const float *q = mov + (size_t)Y * w + X;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) m0[j] = __ldg(q + j), m1[j] = __ldg(q + w + j);
-        } else {
-            const bool yt = Y >= 0 && Y < h, yb = Y + 1 >= 0 && Y + 1 < h;
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const bool xin = X + j >= 0 && X + j < w;
-                m0[j] = (yt && xin) ? __ldg(mov + (size_t)Y * w + X + j) : 0.f;             // zero fill, ICA.py:240-243
-                m1[j] = (yb && xin) ? __ldg(mov + (size_t)(Y + 1) * w + X + j) : 0.f;
+                for (int j = 0; j < 5; ++j) m[r][j] = __ldg(q + r * w + j);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const bool yin = Y + r >= 0 && Y + r < h;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const bool xin = X + j >= 0 && X + j < w;
+                    m[r][j] = (yin && xin) ? __ldg(mov + (size_t)(Y + r) * w + X + j) : 0.f;   // zero fill, ICA.py:240-243
+                }
             }
         }
         float B0 = 0.f, B1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float top = m0[k] + (m0[k + 1] - m0[k]) * frx;
-            const float bot = m1[k] + (m1[k + 1] - m1[k]) * frx;
-            const float gt = (top + (bot - top) * fry) - rc[k];
-            B0 += -gx[k] * gt;
-            B1 += -gy[k] * gt;
-        }
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float top = m[r][k] + (m[r][k + 1] - m[r][k]) * frx;
+                const float bot = m[r + 1][k] + (m[r + 1][k + 1] - m[r + 1][k]) * frx;
+                const float gt = (top + (bot - top) * fry) - rc[r][k];
+                B0 += -gx[r][k] * gt;
+                B1 += -gy[r][k] * gt;
+            }
         B0 = warp_sum(B0), B1 = warp_sum(B1);
-        float(*red)[8] = s_red[it & 1];
+        float(*red)[4] = s_red[it & 1];
         if ((tid & 31) == 0) red[0][tid >> 5] = B0, red[1][tid >> 5] = B1;
         __syncthreads();
         float b0 = red[0][0], b1 = red[1][0];
 #pragma unroll
-        for (int k = 1; k < 8; ++k) b0 += red[0][k], b1 += red[1][k];
+        for (int k = 1; k < 4; ++k) b0 += red[0][k], b1 += red[1][k];
         ax += det_inv * (A11 * b0 - A01 * b1);                                  // ICA.py:268-272
         ay += det_inv * (-A10 * b0 + A00 * b1);
     }
@@ -509,9 +516,9 @@ extern "C" int hhsr_ica(const float *ref, const float *gradx, const float *grady
         case 16: ica_kernel<16, 1, 256><<<grid, 256, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter); break;
         case 32:
             if (ref_w % 4 == 0 && (uintptr_t)ref % 16 == 0 && (uintptr_t)gradx % 16 == 0 && (uintptr_t)grady % 16 == 0)
-                ica32_kernel<true><<<grid, 256, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter);
+                ica32_kernel<true><<<grid, 128, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter);
             else
-                ica32_kernel<false><<<grid, 256, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter);
+                ica32_kernel<false><<<grid, 128, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter);
             break;
         case 64: ica_kernel<64, 2, 256><<<grid, 256, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter); break;
         default: return unsupported("ICA kernel for this tile size not implemented (ICA.py:100)");

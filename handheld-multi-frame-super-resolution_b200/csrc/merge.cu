@@ -638,7 +638,9 @@ template <bool ISO>
 __device__ __forceinline__ bool ref_pixel(const float *__restrict__ raw, const float *__restrict__ covs, const MergeGeom &g, int ox,
                                           int oy, const double *__restrict__ acc_rob, int max_frame_count, int rad_max,
                                           float max_multiplier, float (&val)[3], float (&acc)[3]) {
-    const float pos_y = (float)((double)oy / g.scale), pos_x = (float)((double)ox / g.scale);   // :113-114
+    // :113-114; for power-of-two scales the multiplication by the exact reciprocal is the same correctly-rounded value
+    const float pos_y = g.pow2 ? (float)((double)oy * g.inv_scale) : (float)((double)oy / g.scale);
+    const float pos_x = g.pow2 ? (float)((double)ox * g.inv_scale) : (float)((double)ox / g.scale);
     const float kS = -0.72134752044448170368f;   // -0.5 * log2(e)
     float qxx, qxy, qyy;
     if (ISO) {

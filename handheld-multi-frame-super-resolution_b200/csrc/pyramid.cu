@@ -39,6 +39,40 @@ __global__ void grey_band_mask_kernel(float2 *__restrict__ spec, int H, int W, i
     }
 }
 
+// Same mask for the layout torch.fft.rfft2 actually returns on CUDA (ky contiguous: sy == 1): one CTA row per kx, so the
+// two kx keep-flags are CTA-uniform (about half of the columns are zero as a whole), two ky per thread and one 16-byte
+// store when both vanish.
+__global__ void __launch_bounds__(128) grey_band_mask_cols_kernel(float2 *__restrict__ spec, int H, int W, long long sx) {
+    const int kx = blockIdx.y, ky0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (ky0 >= H) return;
+    const bool kxa = band_keep(kx, W), kxb = band_keep(W - kx, W);
+    float2 *p = spec + (long long)kx * sx + ky0;
+    float m[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int ky = ky0 + j;
+        const float a = (kxa && ky < H && band_keep(ky, H)) ? 0.5f : 0.f;
+        const float b = (kxb && ky < H && band_keep(H - ky, H)) ? 0.5f : 0.f;
+        m[j] = a + b;
+    }
+    const bool pair = ky0 + 1 < H;
+    if (pair && m[0] == 0.f && m[1] == 0.f && (((uintptr_t)p) & 15) == 0) {
+        *reinterpret_cast<float4 *>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (j == 1 && !pair) break;
+        if (m[j] == 0.f)
+            p[j] = make_float2(0.f, 0.f);
+        else if (m[j] != 1.f) {
+            float2 v = p[j];
+            v.x *= m[j], v.y *= m[j];
+            p[j] = v;
+        }
+    }
+}
+
 __global__ void pad_circular_kernel(const float *__restrict__ src, int h, int w, float *__restrict__ dst, int hp, int wp) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= wp || y >= hp) return;
@@ -114,6 +148,11 @@ extern "C" int hhsr_grey_band_mask(float *spec, int H, int W, long long stride_y
     HHSR_REQUIRE((uintptr_t)spec % 8 == 0, "spectrum must be 8-byte aligned");
     HHSR_REQUIRE(stride_y > 0 && stride_x > 0, "strides must be positive");
     const int Wc = W / 2 + 1;
+    if (stride_y == 1) {
+        dim3 block(128), grid(ceil_div(ceil_div(H, 2), 128), Wc);
+        grey_band_mask_cols_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2 *>(spec), H, W, stride_x);
+        return launch_status("grey_band_mask");
+    }
     const int xfast = stride_x <= stride_y;
     const int nfast = xfast ? Wc : H, nslow = xfast ? H : Wc;
     dim3 block(128), grid(ceil_div(nfast, 128), nslow);

@@ -34,10 +34,9 @@ __device__ __forceinline__ void guide_rgb(const float *__restrict__ raw, int W, 
     for (int k = 0; k < 4; ++k) {
         const int c = (p.cfa >> (2 * k)) & 3;
         const double v = (double)q[k] * p.inv_wb[c];
-        if (c == 1)
-            g += v;
-        else
-            out[c] = (float)v;
+        if (c == 1) g += v;
+        if (c == 0) out[0] = (float)v;     // selects, not out[c]: a run-time index would put the array in local memory
+        if (c == 2) out[2] = (float)v;
     }
     out[1] = (float)(g * 0.5);
 }
