@@ -4,39 +4,29 @@
 // utils.py:62-120 (divide, add).  HBM-bound: per comp frame the accumulators num/den [Hs][Ws][3] f32 are read and
 // written once (48 B per HR pixel) and raw/r/covariances are read once (12 B per LR pixel) — see DESIGN.md.
 //
-// Layout / mapping: one thread owns VEC=4 consecutive HR pixels of one row, so its slice of each accumulator is
-// 12 consecutive floats = 3 x float4 (the [.,.,3] interleaving is part of the boundary: main() returns it).
-// LR-side gathers (raw 3x3 taps, 4 covariance quads, r, tile flow) go through the read-only L1/L2 path; they
-// are reused ~36x across neighbouring HR pixels.
+// Layout / mapping: one thread owns 4 consecutive HR pixels of one row, so its slice of each accumulator is
+// 12 consecutive floats = 3 x 16 bytes (the [.,.,3] interleaving is part of the boundary: main() returns it).
+// LR-side gathers (raw 3x3 taps, covariance quads, r, tile flow) go through the read-only L1/L2 path; they are
+// reused ~36x across neighbouring HR pixels.
 //
-// Arithmetic: the reference does all position/weight math in float64 by accident.  Here the
-// sub-pixel position is formed exactly as the reference does it (float64: (hr+0.5)/scale + flow, truncation),
-// then reduced to tap-relative float32 offsets; weights are float32 with ex2.approx.  merge_ref runs once per
-// burst and keeps the reference's float64 arithmetic literally.
-// Compiled with -fmad=false (csrc/Makefile): every fused multiply-add in this file is written explicitly, so the
-// generic, fast-path and batched kernels round identically (bit-equal results) whatever the inlining context.
+// Kernels:
+//   accumulate_pow2_kernel  scales 1, 2, 4 (the benchmark path): exact float32 position split, no float64; the
+//                           accumulators are updated by fire-and-forget 16-byte L2 reductions (never loaded by the SM);
+//   accumulate_kernel       any scale: the reference's float64 position per pixel, float4 load/add/store;
+//   accumulate_batch_kernel K frames per pass over the accumulators;
+//   accumulate_ref_kernel   the reference frame (+ fused divide, + the frame-sharded peer sum, hhsr_reduce_merge_ref).
+// All of them share the per-pixel device functions below and the update  acc <- add.ftz(acc, r * sum)  and are
+// bit-equal where their domains overlap (tests/test_gpu_parity.py).  Compiled with -fmad=false (csrc/Makefile): every
+// fused multiply-add in this file is written explicitly, so the kernels round identically whatever the inlining.
 #include "common.cuh"
 #include <cstdlib>
 
-// tuning knobs (see profiles/): resident CTAs per SM the register allocator must allow, and whether a thread keeps
-// the four covariance quads of its previous pixel in registers
+// resident CTAs per SM the register allocator must allow (measured optimum, profiles/merge_accumulate_r01_ncu.md)
 #ifndef HHSR_MERGE_MINBLOCKS
 #define HHSR_MERGE_MINBLOCKS 5
 #endif
 #ifndef HHSR_MERGE_POW2_MINBLOCKS
 #define HHSR_MERGE_POW2_MINBLOCKS 4
-#endif
-#ifndef HHSR_MERGE_RMW_END
-#define HHSR_MERGE_RMW_END 0     // 1: read-modify-write the whole 12-float slice after the fourth pixel
-#endif
-#ifndef HHSR_MERGE_PREFETCH
-#define HHSR_MERGE_PREFETCH 1
-#endif
-#ifndef HHSR_MERGE_BLOCK_Y
-#define HHSR_MERGE_BLOCK_Y 8
-#endif
-#ifndef HHSR_MERGE_REUSE_QUADS
-#define HHSR_MERGE_REUSE_QUADS 0
 #endif
 
 namespace hhsr {
@@ -248,7 +238,7 @@ __device__ __forceinline__ void merge_pixel(const MergeFrame &f, const MergeGeom
         float frx, fry;
         cov_coord(cj, tx, g.cw, fx0, cx1, frx);
         cov_coord(ci, ty, g.ch, fy0, cy1, fry);
-        if (!HHSR_MERGE_REUSE_QUADS || fx0 != cq.fx0 || fy0 != cq.fy0) {     // neighbouring HR pixels mostly share their four quads
+        {
             const float4 *c4 = reinterpret_cast<const float4 *>(f.covs);
             const float4 *r0 = c4 + (unsigned)fy0 * (unsigned)g.cw, *r1 = c4 + (unsigned)cy1 * (unsigned)g.cw;
             cq.tr = __ldg(r0 + fx0), cq.tl = __ldg(r0 + cx1), cq.br = __ldg(r1 + fx0), cq.bl = __ldg(r1 + cx1);
@@ -444,7 +434,7 @@ __device__ __forceinline__ void resolve_rggb(bool sy, bool sx, const float (&v)[
 }
 
 template <bool ISO, int K, bool STORE>
-__global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_kernel(const __grid_constant__ MergeFrame f,
+__global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_kernel(const __grid_constant__ MergeFrame f,
                                                                                      const __grid_constant__ MergeGeom g,
                                                                                      float *__restrict__ num,
                                                                                      float *__restrict__ den) {
@@ -454,7 +444,7 @@ __global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBL
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (hr_i >= g.Hs || j0 >= g.Ws) return;
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
-    if (HHSR_MERGE_PREFETCH && !STORE && (threadIdx.x & 1) == 0) {
+    if (!STORE && (threadIdx.x & 1) == 0) {   // pre-touch the lines the L2 reductions will hit
         prefetch_l2(num + base);
         prefetch_l2(den + base);
         prefetch_l2(num + base + 23);
@@ -538,9 +528,8 @@ __global__ void __launch_bounds__(32 * HHSR_MERGE_BLOCK_Y, HHSR_MERGE_POW2_MINBL
         resolve_rggb(sy, sx, a, acc);
 #pragma unroll
         for (int c = 0; c < 3; ++c) n[3 * p + c] = val[c], d[3 * p + c] = acc[c];
-        if (HHSR_MERGE_RMW_END ? (p == 3) : (p >= 1))
-#pragma unroll
-        for (int q = (HHSR_MERGE_RMW_END ? 0 : p - 1); q <= p - 1; ++q) {   // float4 number q of the 12-float slice is complete
+        if (p >= 1) {   // float4 number p-1 of the 12-float slice is complete
+            const int q = p - 1;
             rmw4<STORE>(num + base + 4 * q, rr[(4 * q) / 3], n[4 * q], rr[(4 * q + 1) / 3], n[4 * q + 1], rr[(4 * q + 2) / 3],
                  n[4 * q + 2], rr[(4 * q + 3) / 3], n[4 * q + 3]);
             rmw4<STORE>(den + base + 4 * q, rr[(4 * q) / 3], d[4 * q], rr[(4 * q + 1) / 3], d[4 * q + 1], rr[(4 * q + 2) / 3],
@@ -893,8 +882,7 @@ static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num
     dim3 block(32, 8);
     const int k = b.K == 1 ? pow2_fast_shift(g) : -1;
     if (k >= 0) {
-        block = dim3(32, HHSR_MERGE_BLOCK_Y);
-        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, HHSR_MERGE_BLOCK_Y));
+        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8));
         if (k == 0) launch_pow2<0, STORE>(b.f[0], g, num, den, iso, grid, block, st);
         if (k == 1) launch_pow2<1, STORE>(b.f[0], g, num, den, iso, grid, block, st);
         if (k == 2) launch_pow2<2, STORE>(b.f[0], g, num, den, iso, grid, block, st);

@@ -479,8 +479,9 @@ __global__ void __launch_bounds__(RTX *RTY, 8) robustness_kernel(const float *__
             }
         return;
     }
+    // 32-bit element offsets (one IMAD.WIDE per row pointer, immediates for the columns); 7 planes of a 50 MP frame fit
     const float *win = comp_lr + (((y0 >> 1) + s.dy0) * w + ((x0 >> 1) + s.dx0));
-    const unsigned o = (unsigned)y0 * (unsigned)W + x0;
+    const int o = y0 * W + x0, iplane = H * W, ilplane = h * w;
     float d_sq[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     unsigned finite = 0;   // bit i*4+j: reference mean of channel 0 is finite (not in the +inf band)
 #pragma unroll
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(RTX *RTY, 8) robustness_kernel(const float *__
         float col[2][5] = {{0.f, 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const float *row = win + c * lplane + m * w;
+            const float *row = win + (c * ilplane + m * w);
             const float w0 = s.wy[0][m], w1 = s.wy[1][m];
 #pragma unroll
             for (int n = 0; n < 5; ++n) {
@@ -499,8 +500,8 @@ __global__ void __launch_bounds__(RTX *RTY, 8) robustness_kernel(const float *__
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const float4 rm = __ldg(reinterpret_cast<const float4 *>(ref_means + o + c * plane + i * W));
-            const float4 dt = __ldg(reinterpret_cast<const float4 *>(terms + o + c * plane + i * W));
+            const float4 rm = __ldg(reinterpret_cast<const float4 *>(ref_means + (o + c * iplane + i * W)));
+            const float4 dt = __ldg(reinterpret_cast<const float4 *>(terms + (o + c * iplane + i * W)));
             const float rmv[4] = {rm.x, rm.y, rm.z, rm.w}, dtv[4] = {dt.x, dt.y, dt.z, dt.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -515,12 +516,12 @@ __global__ void __launch_bounds__(RTX *RTY, 8) robustness_kernel(const float *__
     const float S = s.S;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const float4 sg = __ldg(reinterpret_cast<const float4 *>(terms + o + 3 * plane + i * W));
+        const float4 sg = __ldg(reinterpret_cast<const float4 *>(terms + (o + 3 * iplane + i * W)));
         const float sgv[4] = {sg.x, sg.y, sg.z, sg.w};
         float out[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) out[j] = ((finite >> (i * 4 + j)) & 1u) ? robustness_finish(d_sq[i][j], sgv[j], S, p.t) : 0.f;
-        *reinterpret_cast<float4 *>(R + o + i * W) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4 *>(R + (o + i * W)) = make_float4(out[0], out[1], out[2], out[3]);
     }
 }
 
