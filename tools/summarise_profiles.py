@@ -27,11 +27,11 @@ def launches():
         a[1] += float(r[iv].replace(",", "")) / 1e3      # ns -> us
     total = sum(v[1] for v in agg.values())
     ours = sum(v[1] for k, v in agg.items() if "hhsr::" in k)
-    out = ["# ncu launch list — `python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (20x12MP_s2, 1xB200), round %s" % tag[1:],
+    out = ["# ncu launch list — `python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e` (20x12MP_s2, 1xB200), round %s" % tag[1:],
            "",
            "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_%s.csv "
            "python bench.py --steps 1 --warmup 3 --no-cpu-baseline`" % tag,
-           "(warm-up steps, the timed resident step, the host-buffer (e2e) steps and the burst generation are all in the list; "
+           "(warm-up steps, the timed resident step, the burst generation are all in the list; "
            "per-launch times are cold-cache and serialised: compare SHARES).", "",
            "| kernel | launches | total ms | avg us | share |", "|---|---:|---:|---:|---:|"]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:34]:
