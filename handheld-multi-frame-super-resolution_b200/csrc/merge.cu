@@ -538,6 +538,165 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// EXPERIMENT (HHSR_MERGE_BULK=1): same arithmetic as accumulate_pow2_kernel, but the accumulators are updated by the
+// TMA engine.  A warp owns 128 consecutive HR pixels of a row = 1536 contiguous bytes of each accumulator; its threads
+// park their products r * sum in shared memory and lane 0 issues ONE bulk asynchronous reduction per accumulator
+// (cp.reduce.async.bulk.global.shared::cta.add.f32, or a bulk store for the initialising first frame), so the SM issues
+// 2 bulk operations per warp instead of 192 16-byte reductions and the L2 receives whole 128-byte lines.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_reduce_add_f32(float *gdst, const float *ssrc, unsigned bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(float *gdst, const float *ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+
+// border / generic threads of the bulk kernel: products of the four pixels straight into the warp's staging rows
+template <bool ISO, bool STORE>
+__device__ __noinline__ void border_products_to_smem(const MergeFrame *f, const MergeGeom *g, int hr_i, int j0, float *sn, float *sd) {
+    RowCtx rc;
+    rc.lr_y = lr_coord(hr_i, g->scale, g->inv_scale, g->pow2);
+    const int ily = (int)rc.lr_y;
+    rc.py = tile_of(ily, *g), rc.i_r = min(ily, g->H - 1);
+    rc.tile_x = -1;
+    CovQuads cq;
+    cq.fx0 = cq.fy0 = -1;
+    for (int p = 0; p < 4; ++p) {
+        float val[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
+        const float r = (j0 + p < g->Ws) ? merge_hr_pixel<ISO>(*f, *g, j0 + p, rc, cq, val, acc) : 0.0f;
+        for (int c = 0; c < 3; ++c) {
+            sn[3 * p + c] = STORE ? add_ftz(0.f, r, val[c]) : r * val[c];
+            sd[3 * p + c] = STORE ? add_ftz(0.f, r, acc[c]) : r * acc[c];
+        }
+    }
+}
+
+template <bool ISO, int K, bool STORE>
+__global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_bulk_kernel(const __grid_constant__ MergeFrame f,
+                                                                                          const __grid_constant__ MergeGeom g,
+                                                                                          float *__restrict__ num,
+                                                                                          float *__restrict__ den) {
+    constexpr int SH = K + 1, MASK = (1 << SH) - 1;
+    constexpr float INV = 1.0f / (float)(1 << SH);
+    __shared__ __align__(128) float s_n[8][384];
+    __shared__ __align__(128) float s_d[8][384];
+    const int warp = threadIdx.y, lane = threadIdx.x;
+    const int hr_i = blockIdx.y * 8 + warp;
+    const int jw = blockIdx.x * 128, j0 = jw + lane * 4;
+    if (hr_i >= g.Hs) return;                       // warp-uniform
+    const bool active = j0 < g.Ws;
+    const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
+    float *sn = &s_n[warp][lane * 12], *sd = &s_d[warp][lane * 12];
+    if (active) {
+        if (!STORE && (lane & 1) == 0) {
+            prefetch_l2(num + base);
+            prefetch_l2(den + base);
+            prefetch_l2(num + base + 23);
+            prefetch_l2(den + base + 23);
+        }
+        const int W = g.W, cw = g.cw;
+        const int n2 = 2 * hr_i + 1;
+        const int by = n2 >> SH;
+        const float qy = (float)(n2 & MASK) * INV;
+        const int bx0 = j0 >> K;
+        const float2 fl = __ldg(reinterpret_cast<const float2 *>(f.flow) + ((by >> g.ts_shift) * g.nx + (bx0 >> g.ts_shift)));
+        const float fiy = truncf(fl.y), fix = truncf(fl.x);
+        const float ffy = fl.y - fiy, ffx = fl.x - fix;
+        int ly;
+        float ty;
+        split_q(qy, ffy, ly, ty);
+        const int ci = by + (int)fiy + ly;
+        const int bx = bx0 + (int)fix;
+        int cj[4];
+        float tx[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int bp = (2 * p + 1) >> SH;
+            const float qp = (float)((2 * p + 1) & MASK) * INV;
+            int lx;
+            split_q(qp, ffx, lx, tx[p]);
+            cj[p] = bx + bp + lx;
+        }
+        if (!(ci >= 1 && ci <= g.H - 2 && cj[0] >= 1 && cj[3] <= W - 2 && g.cfa.bayer && g.cfa.dup == 1)) {
+            border_products_to_smem<ISO, STORE>(&f, &g, hr_i, j0, sn, sd);
+        } else {
+            const int red_at = ((g.cfa.packed & 3) == 0) ? 0 : (((g.cfa.packed >> 2) & 3) == 0) ? 1 : (((g.cfa.packed >> 4) & 3) == 0) ? 2 : 3;
+            const bool sy = ((ci + (red_at >> 1)) & 1) != 0;
+            const int px0 = red_at & 1;
+            const int orow = ci * W;
+            const float *rrow = f.r + (by * W + bx0);
+            const int oqy = ((ci - 1) >> 1) * cw;
+            const float fry = fmaf(0.5f, ty, (ci & 1) ? 0.0f : 0.5f);
+            constexpr int NCOL = (K == 0) ? 4 : 3;
+            CovCol col[NCOL];
+            const int i0 = (cj[0] - 1) >> 1;
+            if (!ISO) {
+                const float4 *q0 = reinterpret_cast<const float4 *>(f.covs) + (oqy + i0);
+                const float4 *q1 = q0 + cw;
+                const int dmax = ((cj[3] - 1) >> 1) - i0;
+                col[0] = cov_column(__ldg(q0), __ldg(q1), fry);
+                col[1] = cov_column(__ldg(q0 + 1), __ldg(q1 + 1), fry);
+#pragma unroll
+                for (int c = 2; c < NCOL; ++c) col[c] = (c <= dmax + 1) ? cov_column(__ldg(q0 + c), __ldg(q1 + c), fry) : col[c - 1];
+            }
+            float n[12], d[12];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int bp = (2 * p + 1) >> SH;
+                float qxx, qxy, qyy;
+                if (ISO) {
+                    qxx = qyy = 2.0f * -0.72134752044448170368f, qxy = 0.0f;
+                } else {
+                    const int dcol = ((cj[p] - 1) >> 1) - i0;
+                    const float frx = fmaf(0.5f, tx[p], (cj[p] & 1) ? 0.0f : 0.5f);
+                    CovCol l = col[0], r = col[1];
+#pragma unroll
+                    for (int c = 1; c < NCOL - 1; ++c)
+                        if (dcol == c) l = col[c], r = col[c + 1];
+                    cov_form_cols(l, r, frx, qxx, qxy, qyy);
+                }
+                float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, a[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+                merge_taps_off(f.raw, W, orow + cj[p], tx[p], ty, qxx, qxy, qyy, v, a);
+                const float rp = __ldg(rrow + bp);
+                const bool sx = ((cj[p] + px0) & 1) != 0;
+                float val[3], acc[3];
+                resolve_rggb(sy, sx, v, val);
+                resolve_rggb(sy, sx, a, acc);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    n[3 * p + c] = STORE ? add_ftz(0.f, rp, val[c]) : rp * val[c];
+                    d[3 * p + c] = STORE ? add_ftz(0.f, rp, acc[c]) : rp * acc[c];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                *reinterpret_cast<float4 *>(sn + 4 * q) = make_float4(n[4 * q], n[4 * q + 1], n[4 * q + 2], n[4 * q + 3]);
+                *reinterpret_cast<float4 *>(sd + 4 * q) = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk engine
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned bytes = (unsigned)min(128, g.Ws - jw) * 12u;
+        float *gn = num + ((size_t)hr_i * g.Ws + jw) * 3, *gd = den + ((size_t)hr_i * g.Ws + jw) * 3;
+        if (STORE) {
+            bulk_store(gn, s_n[warp], bytes);
+            bulk_store(gd, s_d[warp], bytes);
+        } else {
+            bulk_reduce_add_f32(gn, s_n[warp], bytes);
+            bulk_reduce_add_f32(gd, s_d[warp], bytes);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging rows stay valid until they have been read
+    }
+}
+
 // K comp frames in one pass over the accumulators (B200 addition).  The slice is loaded first and the frames are
 // added in list order, so the result is bit-identical to K single-frame launches.
 template <bool ISO, int VEC>
@@ -870,6 +1029,14 @@ static int pow2_fast_shift(const MergeGeom &g) {
 template <int K, bool STORE>
 static void launch_pow2(const MergeFrame &f, const MergeGeom &g, float *num, float *den, int iso, dim3 grid, dim3 block,
                         cudaStream_t st) {
+    const char *e = std::getenv("HHSR_MERGE_BULK");
+    if (e && e[0] == '1') {      // experiment: accumulator traffic through the TMA engine (see accumulate_pow2_bulk_kernel)
+        if (iso)
+            accumulate_pow2_bulk_kernel<true, K, STORE><<<grid, block, 0, st>>>(f, g, num, den);
+        else
+            accumulate_pow2_bulk_kernel<false, K, STORE><<<grid, block, 0, st>>>(f, g, num, den);
+        return;
+    }
     if (iso)
         accumulate_pow2_kernel<true, K, STORE><<<grid, block, 0, st>>>(f, g, num, den);
     else

@@ -431,6 +431,38 @@ def test_merge_pow2_fast_path_equals_generic(scale, cfa):
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (scale, cfa, kern)
 
 
+@pytest.mark.parametrize("scale", [1, 2, 4])
+def test_merge_bulk_variant_equals_default(scale):
+    """HHSR_MERGE_BULK=1 (accumulators updated by bulk asynchronous reductions from shared memory — the TMA engine —
+    instead of per-thread 16-byte L2 reductions) must give the same accumulators as the default kernel, also for the
+    initialising first frame and for a width that leaves the last warp partly outside the image."""
+    from handheld_super_resolution import merge as MG
+    g = torch.Generator(device="cuda").manual_seed(40 + scale)
+    H, W, ts = 96, 208, 16          # W * scale is not a multiple of 128
+    raw = torch.rand((H, W), device="cuda", generator=g)
+    flow = (torch.rand((H // ts, W // ts, 2), device="cuda", generator=g) - 0.5) * 8.0
+    e = torch.rand((H // 2, W // 2, 3), device="cuda", generator=g)
+    k1, k2, th = 0.2 + 2.0 * e[..., 0], 0.2 + 2.0 * e[..., 1], 6.2832 * e[..., 2]
+    c, s_ = torch.cos(th), torch.sin(th)
+    covs = torch.stack([k1 * k1 * c * c + k2 * k2 * s_ * s_, (k1 * k1 - k2 * k2) * c * s_, (k1 * k1 - k2 * k2) * c * s_,
+                        k1 * k1 * s_ * s_ + k2 * k2 * c * c], dim=-1).reshape(H // 2, W // 2, 2, 2).contiguous()
+    r = torch.rand((H, W), device="cuda", generator=g)
+    cfg = attr_cfg(scale=scale, tile_size=ts)
+    outs = []
+    for bulk in ("0", "1"):
+        os.environ["HHSR_MERGE_BULK"] = bulk
+        try:
+            num = torch.full((scale * H, scale * W, 3), float("nan"), device="cuda")
+            den = torch.full_like(num, 7.0)
+            MG.merge(raw, flow, covs, r, num, den, CFA, cfg, init=True)
+            MG.merge(raw, flow * 0.5, covs, r, num, den, CFA, cfg)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("HHSR_MERGE_BULK", None)
+        outs.append((num, den))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("shape", [(64, 96), (70, 100), (37, 53), (5, 8), (3000, 4000)])
 def test_local_min_against_torch(shape):
     """5x5 edge-replicated minimum (robustness.py:641-687): vectorised kernel (W % 4 == 0) and scalar fallback against
