@@ -55,6 +55,20 @@ def reduce_scatter_accumulators(num, den, acc_rob=None, group=None):
     return (rank * rows, (rank + 1) * rows), gather
 
 
+def p2p_row_slices(Hs, world):
+    """Row slices [(begin, end)] of the fused peer-memory reduction.  Rank 0 also RECEIVES every other rank's finished
+    slice (half the bytes of the num + den it would otherwise pull), so it takes a slice half as tall: inbound NVLink
+    bytes are then equal on all ranks ((G-1)(a S + b S/2) = (G-1) b S  =>  a = b/2)."""
+    w = [0.5] + [1.0] * (world - 1)
+    tot = sum(w)
+    edge = [0.0]
+    for x in w:
+        edge.append(edge[-1] + x)
+    cuts = [round(e / tot * Hs) for e in edge]
+    cuts[-1] = Hs
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 class P2PReduce:
     """The reduction point as ONE kernel over NVLink peer memory (mode "p2p"): every rank keeps its private num/den in
     a symmetric-memory buffer (torch.distributed._symmetric_memory: the same allocation mapped into every rank's
@@ -88,17 +102,7 @@ class P2PReduce:
         return cls._cache[key]
 
     def rows(self):
-        """Row slice of this rank.  Rank 0 also RECEIVES every other rank's finished slice (half the bytes of the
-        num + den it would otherwise pull), so it takes a slice half as tall: inbound NVLink bytes are then equal on
-        all ranks ((G-1)(a S + b S/2) = (G-1) b S  =>  a = b/2)."""
-        Hs = self.shape[0]
-        w = [0.5] + [1.0] * (self.world - 1)
-        tot = sum(w)
-        edge = [0]
-        for x in w:
-            edge.append(edge[-1] + x)
-        lo, hi = round(edge[self.rank] / tot * Hs), round(edge[self.rank + 1] / tot * Hs)
-        return lo, (Hs if self.rank == self.world - 1 else hi)
+        return p2p_row_slices(self.shape[0], self.world)[self.rank]
 
     def finalize(self, ref_img, covs, num, den, acc_rob, cfa_pattern, config):
         import ctypes as C

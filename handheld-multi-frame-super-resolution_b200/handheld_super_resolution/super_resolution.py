@@ -6,13 +6,12 @@ import time
 import numpy as np
 import torch
 
-from . import _lib
 from .alignment import align, init_alignment
 from .kernels import estimate_kernels
-from .merge import merge, merge_batch, merge_ref
+from .merge import merge, merge_ref
 from .params import sanitize_config, update_snr_config
 from .robustness import compute_robustness, init_robustness
-from .utils import add_many, divide, timer
+from .utils import add_many, timer
 from .utils_image import compute_grey_images
 
 

@@ -68,3 +68,16 @@ def test_sharded_accumulation_gloo_world2():
         assert p.exitcode == 0
     assert dn < 1e-5 and dd < 1e-5          # float32 summation order only (1e-5)
     assert da < 1e-12
+
+
+def test_p2p_row_slices_tile_the_image():
+    """Row slices of the fused peer-memory reduction: contiguous, cover [0, Hs), rank 0 about half as tall."""
+    from handheld_super_resolution.distributed import p2p_row_slices
+    for world in (1, 2, 3, 4, 8, 16):
+        for Hs in (257, 6000, 9000, 12288):
+            sl = p2p_row_slices(Hs, world)
+            assert sl[0][0] == 0 and sl[-1][1] == Hs and len(sl) == world
+            assert all(a < b for a, b in sl) and all(sl[i][1] == sl[i + 1][0] for i in range(world - 1))
+            if world > 1 and Hs >= 6000:
+                h0, h1 = sl[0][1] - sl[0][0], sl[1][1] - sl[1][0]
+                assert abs(h0 - h1 / 2) <= 1

@@ -1,12 +1,11 @@
 """Diagnostic: medium golden burst through main(); where does the output differ most from the B200 golden?"""
 import os, sys
-import numpy as np, torch
+import numpy as np
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, os.path.join(ROOT, "handheld-multi-frame-super-resolution_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import attr_cfg, load
 from handheld_super_resolution import main
 import handheld_super_resolution.super_resolution as SR
-from handheld_super_resolution import merge as MG
 m = load("medium_pipeline.npz")
 burst = m["burst_u16"].astype(np.float32) / np.float32(16383.0)
 cfg = attr_cfg(m["cfg_json"])
