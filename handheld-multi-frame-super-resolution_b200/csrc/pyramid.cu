@@ -22,13 +22,13 @@ __device__ __forceinline__ bool band_keep(int k, int n) {   // 0 <= k <= n
 // sy/sx: strides of spec in complex elements.  torch.fft.rfft2 on CUDA returns a column-major [H][W/2+1] tensor
 // (strides (1, H)); xfast selects which index runs along threadIdx.x so that accesses stay coalesced either way.
 __global__ void grey_band_mask_kernel(float2 *__restrict__ spec, int H, int W, int Wc, long long sy, long long sx,
-                                      int xfast) {
+                                      int xfast, float scale) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
     const int kx = xfast ? f : s, ky = xfast ? s : f;
     if (kx >= Wc || ky >= H) return;
     const float a = (band_keep(ky, H) && band_keep(kx, W)) ? 0.5f : 0.f;
     const float b = (band_keep(H - ky, H) && band_keep(W - kx, W)) ? 0.5f : 0.f;   // k = n wraps to 0 inside
-    const float m = a + b;   // Re(ifft2(M F)) == ifft2(0.5 (M(k) + M(-k)) F) for a real image
+    const float m = (a + b) * scale;   // Re(ifft2(M F)) == ifft2(0.5 (M(k) + M(-k)) F) for a real image
     float2 *p = spec + (long long)ky * sy + (long long)kx * sx;
     if (m == 0.f)
         *p = make_float2(0.f, 0.f);
@@ -42,7 +42,8 @@ __global__ void grey_band_mask_kernel(float2 *__restrict__ spec, int H, int W, i
 // Same mask for the layout torch.fft.rfft2 actually returns on CUDA (ky contiguous: sy == 1): one CTA row per kx, so the
 // two kx keep-flags are CTA-uniform (about half of the columns are zero as a whole), two ky per thread and one 16-byte
 // store when both vanish.
-__global__ void __launch_bounds__(128) grey_band_mask_cols_kernel(float2 *__restrict__ spec, int H, int W, long long sx) {
+__global__ void __launch_bounds__(128) grey_band_mask_cols_kernel(float2 *__restrict__ spec, int H, int W, long long sx,
+                                                                  float scale) {
     const int kx = blockIdx.y, ky0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (ky0 >= H) return;
     const bool kxa = band_keep(kx, W), kxb = band_keep(W - kx, W);
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(128) grey_band_mask_cols_kernel(float2 *__rest
         const int ky = ky0 + j;
         const float a = (kxa && ky < H && band_keep(ky, H)) ? 0.5f : 0.f;
         const float b = (kxb && ky < H && band_keep(H - ky, H)) ? 0.5f : 0.f;
-        m[j] = a + b;
+        m[j] = (a + b) * scale;
     }
     const bool pair = ky0 + 1 < H;
     if (pair && m[0] == 0.f && m[1] == 0.f && (((uintptr_t)p) & 15) == 0) {
@@ -141,23 +142,24 @@ __global__ void __launch_bounds__(DBX *DBY) gauss_downsample_kernel(const float 
 
 using namespace hhsr;
 
-extern "C" int hhsr_grey_band_mask(float *spec, int H, int W, long long stride_y, long long stride_x,
+extern "C" int hhsr_grey_band_mask(float *spec, int H, int W, long long stride_y, long long stride_x, float scale,
                                    hhsr_stream_t stream) {
     HHSR_REQUIRE(spec, "null pointer");
     HHSR_REQUIRE(H > 0 && W > 0, "non-positive size");
     HHSR_REQUIRE((uintptr_t)spec % 8 == 0, "spectrum must be 8-byte aligned");
     HHSR_REQUIRE(stride_y > 0 && stride_x > 0, "strides must be positive");
+    HHSR_REQUIRE(scale > 0.0f, "scale must be positive");
     const int Wc = W / 2 + 1;
     if (stride_y == 1) {
         dim3 block(128), grid(ceil_div(ceil_div(H, 2), 128), Wc);
-        grey_band_mask_cols_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2 *>(spec), H, W, stride_x);
+        grey_band_mask_cols_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2 *>(spec), H, W, stride_x, scale);
         return launch_status("grey_band_mask");
     }
     const int xfast = stride_x <= stride_y;
     const int nfast = xfast ? Wc : H, nslow = xfast ? H : Wc;
     dim3 block(128), grid(ceil_div(nfast, 128), nslow);
     grey_band_mask_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2 *>(spec), H, W, Wc, stride_y,
-                                                                   stride_x, xfast);
+                                                                   stride_x, xfast, scale);
     return launch_status("grey_band_mask");
 }
 

@@ -19,8 +19,10 @@ def compute_grey_images(img, method):
     h, w = img.shape
     if method == "FFT":
         spec = torch.fft.rfft2(img)
-        _lib.call("hhsr_grey_band_mask", _lib.ptr(spec), h, w, spec.stride(0), spec.stride(1), _lib.stream())
-        return torch.fft.irfft2(spec, s=(h, w))
+        # the 1/(h*w) of the inverse transform is folded into the mask (kept entries are scaled, the rest zeroed) and
+        # the inverse runs unnormalised: one full-image multiply less per frame
+        _lib.call("hhsr_grey_band_mask", _lib.ptr(spec), h, w, spec.stride(0), spec.stride(1), 1.0 / (h * w), _lib.stream())
+        return torch.fft.irfft2(spec, s=(h, w), norm="forward")
     elif method == "decimating":
         out = torch.empty((h // 2, w // 2), dtype=torch.float32, device=img.device)
         _lib.call("hhsr_decimate_to_grey", _lib.ptr(img), h, w, _lib.ptr(out), _lib.stream())

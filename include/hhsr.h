@@ -38,8 +38,11 @@ const char *hhsr_last_error_string(void);
  * (torch.fft.rfft2 / irfft2); this applies the reference's band mask to the half spectrum in place:
  * spec[ky][kx] *= 0.5*(My(ky)Mx(kx) + My(-ky)Mx(-kx)), the Hermitian-symmetrised form of the mask the reference
  * applies to the full shifted spectrum before taking .real.  spec: [H][W/2+1] complex64 (interleaved re,im) with
- * strides (stride_y, stride_x) in complex elements — cuFFT-through-torch hands back a column-major spectrum. */
-int hhsr_grey_band_mask(float *spec, int H, int W, long long stride_y, long long stride_x, hhsr_stream_t stream);
+ * strides (stride_y, stride_x) in complex elements — cuFFT-through-torch hands back a column-major spectrum.
+ * `scale` multiplies the kept entries as well: pass 1/(H*W) with an UNNORMALISED inverse transform
+ * (irfft2(norm="forward")) and the separate normalisation pass over the image disappears; pass 1 otherwise. */
+int hhsr_grey_band_mask(float *spec, int H, int W, long long stride_y, long long stride_x, float scale,
+                        hhsr_stream_t stream);
 
 /* ---- Gaussian pyramid (alignment.py:74-82, utils_image.py:360-391) */
 /* circular padding of the reference grey image to a multiple of the tile size (alignment.py:26-37) */
