@@ -213,8 +213,13 @@ __global__ void __launch_bounds__(256) bm_l2_tiled32_kernel(const float *__restr
             for (int uu = 0; uu < UG; ++uu) red[(v * UG + uu) * 33 + lane] = acc[v][uu];
         __syncwarp();
         if (lane < NV) {
-            double e = 0.0;
-            for (int l = 0; l < 32; ++l) e += red[lane * 33 + l];
+            // four interleaved partial sums (a fixed order too: equal windows still give bit-equal totals) instead of one
+            // chain of 32 dependent float64 additions
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+            const double *q = red + lane * 33;
+#pragma unroll
+            for (int l = 0; l < 32; l += 4) e0 += q[l], e1 += q[l + 1], e2 += q[l + 2], e3 += q[l + 3];
+            const double e = (e0 + e1) + (e2 + e3);
             const int v = lane / UG, u = g * UG + lane % UG;
             if (u < N) s_part[warp * N * N + v * N + u] = e;
         }

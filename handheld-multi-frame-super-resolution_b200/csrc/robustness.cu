@@ -386,6 +386,9 @@ __device__ __forceinline__ float robustness_pixel(const float *__restrict__ comp
 // 2 rows of a thread), so a thread reads a 4x5 window of the comp guide means per channel (instead of 9 taps per
 // pixel) and blends it separably.  Blocks whose windows touch the guide border (clamped taps, +inf band) and
 // tile sizes that are not a multiple of 32 use the per-pixel path.
+#ifndef HHSR_ROB_MINBLOCKS
+#define HHSR_ROB_MINBLOCKS 8
+#endif
 constexpr int RTX = 8, RTY = 16;
 struct RobTile {
     float wx[4][5], wy[2][4];
@@ -416,7 +419,7 @@ __device__ __forceinline__ int axis_window(float fl, int k, float (&wgt)[3]) {
     return ((it + k) >> 1) + off - 1;
 }
 
-__global__ void __launch_bounds__(RTX *RTY, 8) robustness_kernel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
+__global__ void __launch_bounds__(RTX *RTY, HHSR_ROB_MINBLOCKS) robustness_kernel(const float *__restrict__ comp_lr, const float *__restrict__ ref_means,
                                                                  const float *__restrict__ terms, int H, int W,
                                                                  const float *__restrict__ flow, int ny, int nx, int ts,
                                                                  RobParams p, float *__restrict__ R) {
