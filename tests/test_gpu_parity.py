@@ -665,6 +665,30 @@ def test_main_matches_oracle_other_configs():
         assert d < PIPE_TOL, over
 
 
+def test_main_edge_cases_against_oracle():
+    """Edge cases of the burst itself, against the pinned oracle: a burst with NO comp frame (single-frame
+    super-resolution: the accumulators are zero-filled and only merge_ref contributes) and a ragged frame whose sides
+    are not multiples of the tile size (circular padding of the reference pyramid, partial tiles, W % 4 != 0 at
+    scale 1.5 so the scalar merge kernels run)."""
+    import hhsr_oracle as O
+    from handheld_super_resolution import main
+    from handheld_super_resolution.synthetic import synth_burst
+    kw = dict(scale=2, tile_size=16, tile_sizes=[16, 16, 8], factors=[1, 2, 2], metrics=["L2", "L2", "L2"],
+              search_radii=[2, 4, 4])
+    cases = [("no_comp", synth_burst(1, 96, 128, seed=6, quantize_bits=12)[0], kw),
+             ("ragged", synth_burst(3, 106, 150, seed=7, max_shift=2.0, quantize_bits=12)[0], dict(kw, scale=1.5))]
+    for name, burst, k in cases:
+        want, dbg = O.main(burst[0], burst[1:], plain_cfg(**k))
+        out, _ = main(burst[0], burst[1:], attr_cfg(**k))
+        got = host(out)
+        assert got.shape == want.shape
+        noise = dbg["den"] < 1e-30
+        got = np.where(noise & np.isfinite(want), want, got)
+        d = maxdiff(got, want)
+        record("main_edge_%s" % name, d)
+        assert d < PIPE_TOL, name
+
+
 def test_properties_full_size():
     """Size-independent properties at a BASELINE.json shape (12 MP, scale 2, 3 frames):
     (1) identical frames and zero flow -> r == 1 outside the 3-px band and output ~ demosaiced reference;
