@@ -75,6 +75,39 @@ __global__ void __launch_bounds__(RBX *RBY) guide_stats_kernel(const float *__re
     }
 }
 
+// The two halves of guide_stats_kernel as stand-alone stages of the reference API (robustness.py:173-226, 228-294);
+// same arithmetic in the same order, so their composition is bit-equal to the fused kernel.
+__global__ void __launch_bounds__(RBX *RBY) guide_image_kernel(const float *__restrict__ raw, int W, int h, int w, GuideParams p,
+                                                               float *__restrict__ guide) {
+    const int x = blockIdx.x * RBX + threadIdx.x, y = blockIdx.y * RBY + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float rgb[3];
+    guide_rgb(raw, W, y, x, p, rgb);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) guide[((size_t)c * h + y) * w + x] = rgb[c];
+}
+
+__global__ void __launch_bounds__(RBX *RBY) local_stats_kernel(const float *__restrict__ guide, int h, int w,
+                                                               float *__restrict__ means, float *__restrict__ vars) {
+    const int x = blockIdx.x * RBX + threadIdx.x, y = blockIdx.y * RBY + threadIdx.y, c = blockIdx.z;
+    if (x >= w || y >= h) return;
+    const float *g = guide + (size_t)c * h * w;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = -1; i <= 1; ++i)
+#pragma unroll
+        for (int j = -1; j <= 1; ++j) {
+            const float v = __ldg(g + (size_t)min(max(y + i, 0), h - 1) * w + min(max(x + j, 0), w - 1));   // clamp, :287-288
+            s1 += v;
+            s2 = __fmaf_rn(v, v, s2);
+        }
+    const double ninth = 1.0 / 9.0;
+    const double m = (double)s1 * ninth;
+    const size_t o = ((size_t)c * h + y) * w + x;
+    means[o] = (float)m;
+    vars[o] = (float)((double)s2 * ninth - m * m);
+}
+
 __device__ __forceinline__ double dodgson(double t) {   // utils_image.py:398-406
     const double a = fabs(t);
     if (a <= 0.5) return -2.0 * a * a + 1.0;
@@ -625,6 +658,33 @@ extern "C" int hhsr_guide_stats(const float *raw, int H, int W, const int *cfa_h
     dim3 block(RBX, RBY), grid(ceil_div(w, RBX), ceil_div(h, RBY));
     guide_stats_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(raw, W, h, w, p, means, vars);
     return launch_status("guide_stats");
+}
+
+extern "C" int hhsr_guide_image(const float *raw, int H, int W, const int *cfa_host, const double *wb_host, float *guide,
+                                hhsr_stream_t stream) {
+    HHSR_REQUIRE(raw && cfa_host && wb_host && guide, "null pointer");
+    HHSR_REQUIRE(H >= 2 && W >= 2 && W % 2 == 0, "frame must be at least 2x2 with an even width");
+    HHSR_REQUIRE((uintptr_t)raw % 8 == 0, "raw must be 8-byte aligned");
+    GuideParams p;
+    p.cfa = pack_cfa(cfa_host);
+    for (int k = 0; k < 4; ++k) HHSR_REQUIRE(cfa_host[k] >= 0 && cfa_host[k] <= 2, "cfa entries must be 0, 1 or 2");
+    for (int c = 0; c < 3; ++c) {
+        HHSR_REQUIRE(wb_host[c] != 0.0, "white balance gains of the three colour channels must be non-zero");
+        p.inv_wb[c] = 1.0 / wb_host[c];
+    }
+    const int h = H / 2, w = W / 2;
+    dim3 block(RBX, RBY), grid(ceil_div(w, RBX), ceil_div(h, RBY));
+    guide_image_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(raw, W, h, w, p, guide);
+    return launch_status("guide_image");
+}
+
+extern "C" int hhsr_local_stats(const float *guide, int channels, int h, int w, float *means, float *vars,
+                                hhsr_stream_t stream) {
+    HHSR_REQUIRE(guide && means && vars, "null pointer");
+    HHSR_REQUIRE(h > 0 && w > 0 && channels > 0 && channels <= 65535, "non-positive size");
+    dim3 block(RBX, RBY), grid(ceil_div(w, RBX), ceil_div(h, RBY), channels);
+    local_stats_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(guide, h, w, means, vars);
+    return launch_status("local_stats");
 }
 
 extern "C" int hhsr_upscale_warp_stats(const float *lr, int h, int w, const float *flow, int ny, int nx, int ts,

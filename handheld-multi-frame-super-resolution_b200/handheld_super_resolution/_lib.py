@@ -30,6 +30,8 @@ SIGNATURES = {
     "hhsr_gat": [_P, _Z, _D, _D, _P, _P],
     "hhsr_decimate_to_grey": [_P, _I, _I, _P, _P],
     "hhsr_guide_stats": [_P, _I, _I, _IP, _DP, _P, _P, _P],
+    "hhsr_guide_image": [_P, _I, _I, _IP, _DP, _P, _P],
+    "hhsr_local_stats": [_P, _I, _I, _I, _P, _P, _P],
     "hhsr_upscale_warp_stats": [_P, _I, _I, _P, _I, _I, _I, _P, _P],
     "hhsr_noise_table": [_P, _P, _I, _P, _P],
     "hhsr_ref_stats_terms": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P],

@@ -17,6 +17,28 @@ def compute_guide_stats(raw_img, cfa_pattern, white_balance, need_vars=True):
     return means, vars_
 
 
+def compute_guide_image(raw_img, cfa_pattern, white_balance):
+    """Guide image G [3, H//2, W//2] of a raw frame (Alg. 7, robustness.py:173-226) — the stand-alone stage; the
+    pipeline uses compute_guide_stats, which fuses it with compute_local_stats (bit-equal)."""
+    raw_img = _lib.as_device(raw_img)
+    H, W = raw_img.shape
+    guide = torch.empty((3, H // 2, W // 2), dtype=torch.float32, device=raw_img.device)
+    _lib.call("hhsr_guide_image", _lib.ptr(raw_img), H, W, _lib.cfa_array(cfa_pattern), _lib.wb_array(white_balance),
+              _lib.ptr(guide), _lib.stream())
+    return guide
+
+
+def compute_local_stats(guide_img):
+    """3x3 local mean and variance of the guide image (Alg. 8, robustness.py:228-294): (means, vars) [C, h, w]."""
+    guide_img = _lib.as_device(guide_img)
+    n_channels, h, w = guide_img.shape
+    if n_channels not in (1, 3):
+        raise ValueError("Incoherent number of channel : {}".format(n_channels))
+    means, vars_ = torch.empty_like(guide_img), torch.empty_like(guide_img)
+    _lib.call("hhsr_local_stats", _lib.ptr(guide_img), n_channels, h, w, _lib.ptr(means), _lib.ptr(vars_), _lib.stream())
+    return means, vars_
+
+
 def upscale_warp_stats(local_stats, tile_size=None, flow=None):
     """x2 Dodgson upsampling (+ warp by the tile flow) of a [3,h,w] statistic to [3,2h,2w] (robustness.py:296-418)."""
     local_stats = _lib.as_device(local_stats)

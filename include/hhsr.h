@@ -96,6 +96,12 @@ int hhsr_decimate_to_grey(const float *img, int H, int W, float *out, hhsr_strea
  * vars may be NULL. */
 int hhsr_guide_stats(const float *raw, int H, int W, const int *cfa_host, const double *wb_host, float *means,
                      float *vars, hhsr_stream_t stream);
+/* the two halves of hhsr_guide_stats as stand-alone stages of the reference API: guide image [3][H/2][W/2]
+ * (robustness.py:173-226) and 3x3 edge-replicated mean / variance of a [channels][h][w] image (robustness.py:228-294);
+ * their composition is bit-equal to hhsr_guide_stats. */
+int hhsr_guide_image(const float *raw, int H, int W, const int *cfa_host, const double *wb_host, float *guide,
+                     hhsr_stream_t stream);
+int hhsr_local_stats(const float *guide, int channels, int h, int w, float *means, float *vars, hhsr_stream_t stream);
 /* x2 Dodgson upsampling (+ tile-flow warp when flow != NULL) of a [3][h][w] statistic to [3][2h][2w]
  * (robustness.py:296-418); +inf where the source position leaves the guide image. */
 int hhsr_upscale_warp_stats(const float *lr, int h, int w, const float *flow, int ny, int nx, int ts, float *hr,

@@ -209,6 +209,21 @@ def test_init_robustness(tiny, stage):
     assert maxdiff(host(lm), stage["lmeans_f1"]) < 1e-7 and maxdiff(host(ls), stage["lstds_f1"]) < 1e-7
 
 
+def test_guide_image_and_local_stats_stage_functions(tiny):
+    """compute_guide_image + compute_local_stats (the reference's separate stages) compose bit-equally to the fused
+    compute_guide_stats and match the oracle."""
+    import hhsr_oracle as O
+    from handheld_super_resolution import robustness as RB
+    raw = tiny["burst"][1]
+    guide = RB.compute_guide_image(dev(raw), CFA, WB)
+    means, vars_ = RB.compute_local_stats(guide)
+    fm, fv = RB.compute_guide_stats(dev(raw), CFA, WB)
+    assert torch.equal(means, fm) and torch.equal(vars_, fv)
+    og = O.guide_image(raw, CFA, WB)
+    om, ov = O.local_stats(og)
+    assert maxdiff(host(guide), og) < 1e-7 and maxdiff(host(means), om) < 1e-6 and maxdiff(host(vars_), ov) < 1e-6
+
+
 def test_compute_robustness(tiny, stage):
     from handheld_super_resolution import robustness as RB
     cfg = attr_cfg(tiny["cfg_json"])

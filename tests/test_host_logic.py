@@ -167,3 +167,25 @@ def test_raw_normalisation_host_matches_reference_loop():
         want = O.normalize_raw(raw, cfa, black, white, wb)
         got = RawNormalization(cfa, black, white, wb).apply_numpy(raw)
         assert got.dtype == np.float32 and np.array_equal(got, want)
+
+
+def test_api_surface_matches_the_reference():
+    """The drop-in boundary: every host-side stage function of the reference's hot path exists
+    under the same module and name and takes the reference's positional parameters in the reference's order
+    (tests/golden/api_signatures.json is extracted from the reference sources by make_api_signatures.py); extra
+    keyword parameters with defaults are B200 additions."""
+    import importlib
+    import inspect
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "api_signatures.json")))
+    assert len(ref) == 10
+    for module, sigs in ref.items():
+        mod = importlib.import_module("handheld_super_resolution." + module)
+        for name, sig in sigs.items():
+            assert hasattr(mod, name), "%s.%s is missing" % (module, name)
+            params = inspect.signature(getattr(mod, name)).parameters
+            ours = list(params)
+            n = len(sig["args"])
+            assert ours[:n] == sig["args"], (module, name, sig["args"], ours)
+            for extra in ours[n:]:
+                assert params[extra].default is not inspect.Parameter.empty, (module, name, extra)
