@@ -189,3 +189,34 @@ def test_api_surface_matches_the_reference():
             assert ours[:n] == sig["args"], (module, name, sig["args"], ours)
             for extra in ours[n:]:
                 assert params[extra].default is not inspect.Parameter.empty, (module, name, extra)
+
+
+def test_params_against_reference_golden():
+    """update_snr_config / sanitize_config against what the reference's own params.py does on the same configs
+    (tests/golden/params_cases.json, generated by make_golden_params.py): derived values identical, same accept /
+    reject decisions with the same exception types.  Documented deviation: we additionally reject
+    pyramids whose coarsest level holds no tile, which the reference only notices later."""
+    import json
+    from handheld_super_resolution.config import load_config
+    from handheld_super_resolution.params import sanitize_config, update_snr_config
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "params_cases.json")))
+    for c in g["snr"]:
+        cfg = load_config(overrides=c["over"])
+        update_snr_config(cfg, c["snr"])
+        t, m = cfg.block_matching.tuning, cfg.merging.tuning
+        assert t.tile_size == c["tile_size"] and list(t.tile_sizes) == c["tile_sizes"], c
+        for k in ("k_detail", "k_denoise", "D_th", "D_tr"):
+            assert m[k] == c[k], (c["snr"], k, m[k], c[k])          # bit-identical floats
+    stricter = 0
+    for c in g["sanitize"]:
+        cfg = load_config(overrides=c["over"])
+        try:
+            update_snr_config(cfg, 30.0)
+            sanitize_config(cfg, tuple(c["shape"]))
+            res = "ok"
+        except Exception as e:      # noqa: BLE001
+            res = type(e).__name__
+        if res != c["result"]:
+            assert c["result"] == "ok" and res == "ValueError", (c, res)     # only ever stricter, and only the Q12 check
+            stricter += 1
+    assert stricter <= 1
