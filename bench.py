@@ -35,7 +35,7 @@ WORKLOADS = {   # BASELINE.json configs
 
 
 def make_config(scale, H, W):
-    """configs/default.yaml + the benchmark settings of SURVEY section 8d: tile_size 32 explicit, ISO-100 noise
+    """configs/defaults.yaml + the benchmark settings of SURVEY section 8d: tile_size 32 explicit, ISO-100 noise
     model, RGGB, SNR-derived merge constants (SNR clips to 30 on the synthetic burst)."""
     from handheld_super_resolution.config import Config, load_config
     from handheld_super_resolution.noise_model import run_fast_MC

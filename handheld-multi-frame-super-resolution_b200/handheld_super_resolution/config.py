@@ -7,7 +7,7 @@ import os
 
 import yaml
 
-DEFAULT_YAML = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "configs", "default.yaml")
+DEFAULT_YAML = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "configs", "defaults.yaml")
 
 
 class Config(dict):
@@ -42,7 +42,7 @@ class Config(dict):
 
 
 def load_config(path=None, overrides=None):
-    """configs/default.yaml merged with an optional user YAML and a dict of overrides (run_handheld.py:94-116)."""
+    """configs/defaults.yaml merged with an optional user YAML and a dict of overrides (run_handheld.py:94-116)."""
     cfg = Config.wrap(yaml.safe_load(open(DEFAULT_YAML)))
     if path is not None:
         cfg.merge_with(yaml.safe_load(open(path)) or {})

@@ -44,7 +44,15 @@ def main():
     P = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(P)
     base = yaml.safe_load(open(os.path.join(REF, "configs", "default.yaml")))
-    out = {"snr": [], "sanitize": []}
+    def flat(d, prefix=""):
+        r = {}
+        for k, v in d.items():
+            if isinstance(v, dict):
+                r.update(flat(v, prefix + k + "."))
+            else:
+                r[prefix + k] = v
+        return r
+    out = {"default_config": flat(base), "snr": [], "sanitize": []}
     for snr in [0.5, 6, 6.01, 10, 13.99, 14, 14.01, 18, 22, 22.01, 25.5, 30, 31, 1000]:
         for over in ({}, {"block_matching": {"tuning": {"tile_size": 32}}}, {"merging": {"tuning": {"k_detail": 0.3, "D_tr": 1.1}}}):
             c = Cfg.wrap(copy.deepcopy(base))

@@ -220,3 +220,21 @@ def test_params_against_reference_golden():
             assert c["result"] == "ok" and res == "ValueError", (c, res)     # only ever stricter, and only the Q12 check
             stricter += 1
     assert stricter <= 1
+
+
+def test_default_config_has_the_reference_keys_and_values():
+    """configs/defaults.yaml carries exactly the keys and default values of the reference's configs/default.yaml
+    (flattened in tests/golden/params_cases.json by make_golden_params.py)."""
+    import json
+    from handheld_super_resolution.config import load_config, to_plain
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "params_cases.json")))["default_config"]
+
+    def flat(d, prefix=""):
+        out = {}
+        for k, v in d.items():
+            if isinstance(v, dict):
+                out.update(flat(v, prefix + k + "."))
+            else:
+                out[prefix + k] = v
+        return out
+    assert flat(to_plain(load_config())) == want
