@@ -107,15 +107,28 @@ def as_device(x, dtype=torch.float32):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_HOST_ARRAYS = {}     # small host-side argument arrays, cached by value (they are rebuilt for every launch otherwise)
+
+
+def _cached(kind, values, build):
+    key = (kind, values)
+    arr = _HOST_ARRAYS.get(key)
+    if arr is None:
+        if len(_HOST_ARRAYS) > 256:
+            _HOST_ARRAYS.clear()
+        arr = _HOST_ARRAYS[key] = build(values)
+    return arr
+
+
 def cfa_array(cfa):
     a = np.asarray(cfa.cpu() if isinstance(cfa, torch.Tensor) else cfa).astype(np.int64).reshape(-1)
     if a.size != 4:
         raise ValueError("CFA pattern must be 2x2")
-    return (C.c_int * 4)(*[int(v) for v in a])
+    return _cached("cfa", tuple(int(v) for v in a), lambda v: (C.c_int * 4)(*v))
 
 
 def wb_array(wb):
     a = np.asarray(wb.cpu() if isinstance(wb, torch.Tensor) else wb, dtype=np.float64).reshape(-1)
     if a.size < 3:
         raise ValueError("white balance needs at least 3 gains")
-    return (C.c_double * 3)(*[float(v) for v in a[:3]])
+    return _cached("wb", tuple(float(v) for v in a[:3]), lambda v: (C.c_double * 3)(*v))

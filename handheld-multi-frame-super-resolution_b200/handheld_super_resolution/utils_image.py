@@ -48,6 +48,17 @@ def gaussian_kernel1d(sigma, radius):
     return phi / phi.sum()
 
 
+_TAPS = {}
+
+
+def _downsample_taps(factor):
+    """(radius, float32 taps) of one pyramid level, cached per factor (built per frame and level otherwise)."""
+    if factor not in _TAPS:
+        radius = int(4 * factor * 0.5 + 0.5)
+        _TAPS[factor] = (radius, np.ascontiguousarray(gaussian_kernel1d(factor * 0.5, radius)[::-1].astype(np.float32)))
+    return _TAPS[factor]
+
+
 def cuda_downsample(th_img, kernel="gaussian", factor=2):
     """One pyramid level (utils_image.py:360-391).  th_img: [h,w] (or [1,1,h,w]) CUDA tensor; returns [h2,w2]."""
     if factor == 1:
@@ -56,8 +67,7 @@ def cuda_downsample(th_img, kernel="gaussian", factor=2):
         raise ValueError("please use gaussian kernel")
     img = _lib.as_device(th_img)
     img = img.reshape(img.shape[-2], img.shape[-1])
-    radius = int(4 * factor * 0.5 + 0.5)
-    taps = gaussian_kernel1d(factor * 0.5, radius)[::-1].astype(np.float32)
+    radius, taps = _downsample_taps(int(factor))
     h, w = img.shape
     h2, w2 = (h - 2 * radius) // factor, (w - 2 * radius) // factor
     if h2 < 1 or w2 < 1:
