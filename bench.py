@@ -34,24 +34,41 @@ WORKLOADS = {   # BASELINE.json configs
 }
 
 
-def make_config(scale, H, W):
-    """configs/defaults.yaml + the benchmark settings of SURVEY section 8d: tile_size 32 explicit, ISO-100 noise
-    model, RGGB, SNR-derived merge constants (SNR clips to 30 on the synthetic burst)."""
+def noise_curves():
+    """The reference's own ISO-100 noise curves (data/noise_model_{std,diff}_ISO_100.npy of the reference; SURVEY 8d
+    fixes them as the benchmark input) from the committed copy tests/golden/noise_curves_iso100.npz."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "noise_curves_iso100.npz"))
+    return z["std_curve"], z["diff_curve"]
+
+
+def make_config(scale, H, W, ref_brightness):
+    """configs/defaults.yaml + the benchmark settings of SURVEY section 8d: tile_size 32 explicit, ISO-100 noise model
+    and curves, RGGB, merge constants derived from the SNR exactly as process() derives it
+    (super_resolution.py:261-274: brightness = mean of the reference frame, SNR = brightness / std_curve[...])."""
     from handheld_super_resolution.config import Config, load_config
-    from handheld_super_resolution.noise_model import run_fast_MC
     from handheld_super_resolution.params import sanitize_config, update_snr_config
     from handheld_super_resolution.synthetic import ALPHA_ISO100, BETA_ISO100, CFA_RGGB, WHITE_BALANCE
     cfg = load_config(overrides={"scale": scale, "verbose": 0, "block_matching": {"tuning": {"tile_size": 32}}})
     if min(H, W) < 673:   # default factors need >= 673 px (SURVEY Q12); small plumbing config uses [1,2,2,2]
         cfg.block_matching.tuning.factors = [1, 2, 2, 2]
     cfg.noise_model.alpha, cfg.noise_model.beta = ALPHA_ISO100, BETA_ISO100
-    std_curve, diff_curve = run_fast_MC(ALPHA_ISO100, BETA_ISO100, seed=0, n_patches=20000)
-    update_snr_config(cfg, 30.0)
+    std_curve, diff_curve = noise_curves()
+    update_snr_config(cfg, float(ref_brightness) / std_curve[round(1000 * float(ref_brightness))])
     cfg.exif = Config.wrap({"cfa_pattern": CFA_RGGB, "iso": 100, "white_balance": WHITE_BALANCE})
     cfg.noise_model.std_curve, cfg.noise_model.diff_curve = std_curve, diff_curve
     cfg.accumulated_robustness_denoiser.enabled = False
     sanitize_config(cfg, (H, W))
     return cfg
+
+
+def workload_config(wl_name, wl, n_gpus):
+    """The `config` object of the JSON line — the same for both arms (the reference arm runs a bounded sample of it,
+    described in its cpu_baseline.sample)."""
+    return {"workload": wl_name, **wl, "tile_size": 32, "noise_curves": "reference data/noise_model_*_ISO_100.npy",
+            "snr": "derived from the reference frame as process() does",
+            "parallelism": "single GPU" if n_gpus == 1 else "comp frames sharded over %d GPUs, one reduction point" % n_gpus,
+            "l2": "inputs per step (%.0f MB burst + %.0f MB accumulators) exceed the 126 MB L2; no flush needed"
+                  % (wl["n"] * wl["H"] * wl["W"] * 4 / 1e6, round(wl["scale"] * wl["H"]) * round(wl["scale"] * wl["W"]) * 24 / 1e6)}
 
 
 class ClockSampler:
@@ -97,11 +114,12 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def merge_algorithmic_bytes(H, W, scale, ny, nx):
-    """SURVEY section 8d / DESIGN.md: per comp frame, one accumulator pass: num+den read+write (48 B per HR pixel)
-    + raw, r, covariances (4 + 4 + 16/4 = 12 B per LR pixel) + the tile flow."""
+def merge_algorithmic_bytes(H, W, scale, ny, nx, K=1, init=False):
+    """SURVEY section 8d / DESIGN.md, one merge launch over K comp frames: ONE pass over num+den (24 B per HR pixel
+    written, and read as well unless the launch initialises them) + per frame raw, r, covariances (4 + 4 + 16/4 = 12 B
+    per LR pixel) and the tile flow:  B_batch(K) = HR*24*(1 + [not init]) + K*(LR*12 + tiles*8)  — never K * B_frame."""
     hs, ws = round(scale * H), round(scale * W)
-    return hs * ws * 48 + H * W * 12 + ny * nx * 8
+    return hs * ws * 24 * (1 if init else 2) + K * (H * W * 12 + ny * nx * 8)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -145,7 +163,8 @@ def cpu_sample(wl, n_frames, crop, cores):
     from handheld_super_resolution.config import to_plain
     from handheld_super_resolution.synthetic import synth_burst
     burst, _ = synth_burst(n_frames, crop, crop, seed=0)
-    cfg = to_plain(make_config(wl["scale"], crop, crop))
+    cfg = to_plain(make_config(wl["scale"], crop, crop, float(np.mean(burst[0]))))
+    cfg["noise_model"]["std_curve"], cfg["noise_model"]["diff_curve"] = noise_curves()
     out_mpix = round(wl["scale"] * crop) ** 2 / 1e6
     return burst, cfg, out_mpix * n_frames / wl["n"]
 
@@ -174,7 +193,7 @@ def run_reference_arm(args, wl, wl_name):
     line = {"impl": "reference", "metric": "output MPix/s (20x12MP->48MP burst)", "value": value, "unit": "MPix/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64 mixed (as the reference)",
-            "data": "synthetic", "config": {"workload": wl_name, **wl},
+            "data": "synthetic", "config": workload_config(wl_name, wl, args.gpus),
             "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": nproc, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -197,7 +216,6 @@ def run_cuda_arm(args, wl, wl_name):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, H, W, scale = wl["n"], wl["H"], wl["W"], wl["scale"]
-    cfg = make_config(scale, H, W)
     hs, ws = round(scale * H), round(scale * W)
     # the one reduction point: fused peer-memory kernel (default when it can be set up) or NCCL reduce-scatter
     reduce_mode = args.reduce
@@ -216,6 +234,7 @@ def run_cuda_arm(args, wl, wl_name):
     os.environ["HHSR_SHARD_REDUCE"] = reduce_mode
 
     burst_dev, _ = synth_burst(n, H, W, seed=0, device="cuda", as_numpy=False)      # same burst on every rank
+    cfg = make_config(scale, H, W, burst_dev[0].mean().item())
     burst_host = torch.empty((n, H, W), dtype=torch.float32).pin_memory()
     burst_host.copy_(burst_dev)
     # the same burst as 14-bit sensor counts (black level 1024): the form a DNG decoder hands over
@@ -233,19 +252,27 @@ def run_cuda_arm(args, wl, wl_name):
     d2h_state = {"k": 0, "events": [None, None]}
     torch.cuda.synchronize()
 
-    # per-launch timing of the dominant kernel (merge accumulate) with CUDA events on the launching stream
+    # per-launch timing of the dominant kernel (merge accumulate) with CUDA events on the launching stream:
+    # (frames in the launch, initialising?, start, end) for every merge launch of the timed steps
     merge_events = []
-    orig_merge = SR.merge
+    orig_merge, orig_merge_batch = SR.merge, SR.merge_batch
 
     def timed_merge(*a, **k):
-        if k.get("init"):       # the first comp frame initialises the accumulators (write-only, different byte count):
-            return orig_merge(*a, **k)   # not part of the roofline average of the read-modify-write launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         orig_merge(*a, **k)
         e1.record()
-        merge_events.append((e0, e1))
-    SR.merge = timed_merge
+        merge_events.append((1, bool(k.get("init")), e0, e1))
+
+    def timed_merge_batch(comps, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_merge_batch(comps, *a, **k)
+        e1.record()
+        merge_events.append((len(comps), bool(k.get("init")), e0, e1))
+    SR.merge, SR.merge_batch = timed_merge, timed_merge_batch
+    batch = args.merge_batch if args.merge_batch > 0 else SR.MERGE_BATCH
+    SR.MERGE_BATCH = batch
 
     def step_resident():
         out, _ = main_sharded(burst_dev[0], burst_dev[1:], cfg)
@@ -307,8 +334,19 @@ def run_cuda_arm(args, wl, wl_name):
     launches0 = _lib.launch_count
     ms_res, t0, t1 = timed(step_resident, args.steps)
     launches = (_lib.launch_count - launches0)
-    merge_ms = [a.elapsed_time(b) for a, b in merge_events]
+    merge_launches = [(K, init, a.elapsed_time(b)) for K, init, a, b in merge_events]
     merge_events.clear()
+    # the reference's launch granularity (one comp frame per pass over the accumulators) for comparison: a few steps
+    # with the batching switched off; its read-modify-write launches are the kernel round 1 reported
+    per_frame_ms = []
+    if batch != 1 and world == 1:
+        SR.MERGE_BATCH = 1
+        step_resident()
+        merge_events.clear()
+        timed(step_resident, 2)
+        per_frame_ms = [a.elapsed_time(b) for K, init, a, b in merge_events if not init]
+        merge_events.clear()
+        SR.MERGE_BATCH = batch
     if args.no_e2e:        # profiling runs (ncu replays every launch): the resident step only
         ms_e2e = ms_lat = ms_u16 = float("nan")
         t2 = t1
@@ -320,29 +358,34 @@ def run_cuda_arm(args, wl, wl_name):
         step_e2e(u16=True)
         ms_u16, _, t2 = timed(lambda: step_e2e(u16=True), args.steps)
     clocks = sampler.stop(t0, t2) if rank == 0 else None
-    SR.merge = orig_merge
+    SR.merge, SR.merge_batch = orig_merge, orig_merge_batch
 
     if rank == 0:
         out_mpix = hs * ws / 1e6
         peak, peak_src = measured_peak_gbs()
         ny, nx = -(-H // 32), -(-W // 32)
-        alg = merge_algorithmic_bytes(H, W, scale, ny, nx)
-        avg_merge_ms = float(np.mean(merge_ms)) if merge_ms else float("nan")
-        achieved = alg / (avg_merge_ms * 1e-3) / 1e9
+        # roofline of the merge launches of the timed steps: algorithmic bytes B_batch(K) of every launch / its duration
+        alg_total = sum(merge_algorithmic_bytes(H, W, scale, ny, nx, K, init) for K, init, _ in merge_launches)
+        ms_total = sum(ms for _, _, ms in merge_launches)
+        frames_total = sum(K for K, _, _ in merge_launches)
+        achieved = alg_total / (ms_total * 1e-3) / 1e9 if ms_total > 0 else float("nan")
+        n_launch = max(len(merge_launches), 1)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "merge_traffic_bytes.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(wl_name)
+            traffic = json.load(open(tp)).get("%s_batch%d" % (wl_name, batch))
+        alg1 = merge_algorithmic_bytes(H, W, scale, ny, nx)
+        pf_ms = float(np.mean(per_frame_ms)) if per_frame_ms else None
         line = {
             "metric": "output MPix/s (20x12MP->48MP burst)" if wl_name == "20x12MP_s2" else "output MPix/s",
             "value": out_mpix / (ms_res * 1e-3), "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (f64 sub-pixel positions)", "data": "synthetic",
-            "config": {"workload": wl_name, **wl, "tile_size": 32, "parallelism": "frames sharded over %d GPU(s), %s" % (world, "single GPU" if world == 1 else (
-                           "one fused peer-memory kernel (NVLink pull + sum + merge_ref + divide, image gathered on rank 0)"
-                           if reduce_mode == "p2p" else "one NCCL reduce-scatter + all-gather of the image")),
-                       "l2": "inputs per step (%.0f MB burst + %.0f MB accumulators) exceed the 126 MB L2; no flush needed"
-                             % (n * H * W * 4 / 1e6, hs * ws * 24 / 1e6)},
+            "config": workload_config(wl_name, wl, world),
+            "reduce": None if world == 1 else (
+                "one fused peer-memory kernel (NVLink pull + sum + merge_ref + divide)" if reduce_mode == "p2p"
+                else "one NCCL reduce-scatter + all-gather of the image"),
+            "merge_batch": batch,
             "e2e": {"value": out_mpix / (ms_e2e * 1e-3), "unit": "MPix/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(n * H * W * 4), "d2h_bytes_per_step": int(hs * ws * 3 * 4),
                     "mode": "back-to-back bursts, result D2H double-buffered on a copy stream (overlaps the next burst)",
@@ -351,10 +394,21 @@ def run_cuda_arm(args, wl, wl_name):
                                    "h2d_bytes_per_step": int(n * H * W * 2),
                                    "note": "same call fed with 14-bit sensor counts (uint16), normalised on the device"}},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "accumulate_pow2_kernel (merge, one comp frame per launch)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_merge_ms,
-                         "launches_timed": len(merge_ms)},
+            "roofline": {"kernel": ("accumulate_pow2_batch_kernel (merge, up to %d comp frames per pass over the accumulators)" % batch)
+                                   if batch > 1 else "accumulate_pow2_kernel (merge, one comp frame per launch)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_total / n_launch, "avg_launch_ms": ms_total / n_launch,
+                         "launches_timed": len(merge_launches), "frames_per_launch": frames_total / n_launch,
+                         "ms_per_frame": ms_total / max(frames_total, 1),
+                         "accounting": "B_batch(K) = HR*24*(1 + [not init]) + K*(LR*12 + tiles*8) per launch (SURVEY 8d), "
+                                       "summed over every merge launch of the timed steps / summed CUDA-event durations",
+                         "note": "frame batching removes accumulator traffic: the kernel moves from the HBM roofline to the "
+                                 "issue limit of the tap arithmetic, so the step gets faster while this fraction falls",
+                         "per_frame_kernel": None if pf_ms is None else {
+                             "kernel": "accumulate_pow2_kernel (merge_batch_size=1: one frame per pass, the reference's granularity)",
+                             "achieved": alg1 / (pf_ms * 1e-3) / 1e9, "frac": alg1 / (pf_ms * 1e-3) / 1e9 / peak,
+                             "avg_launch_ms": pf_ms, "algorithmic_bytes_per_launch": alg1, "launches_timed": len(per_frame_ms)}},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -384,6 +438,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="20x12MP_s2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge-batch", type=int, default=0, help="comp frames per pass over the accumulators (0: the package default)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer legs (e2e fields are NaN)")
     ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "reduce_scatter", "allreduce"],
                     help="N > 1: how the frame-sharded accumulators are summed (auto = p2p when available)")

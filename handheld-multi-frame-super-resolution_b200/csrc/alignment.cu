@@ -7,8 +7,21 @@
 // (ica_kernel_{8,16,32,64}).  One CTA per tile; tiles and search windows are staged in shared memory, SSD sums
 // are reduced with warp shuffles.
 #include "common.cuh"
+#include <atomic>
 
 namespace hhsr {
+
+// Opt-in to > 48 KB of dynamic shared memory: a per-device function attribute, set once per (kernel, device) instead of
+// on every launch.  The only process-wide state of the library besides the last-error string: a bit per device.
+template <class Kernel>
+static void ensure_dynamic_smem(Kernel kernel, std::atomic<unsigned long long> &done, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_relaxed) & bit) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 > bytes ? (int)(200 * 1024) : (int)bytes);
+    done.fetch_or(bit, std::memory_order_relaxed);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // gradients + Hessian: one CTA per ts x ts cell of ceil(h/ts) x ceil(w/ts); complete tiles also emit H.
@@ -469,7 +482,8 @@ extern "C" int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const f
     float2 *F2 = reinterpret_cast<float2 *>(flow);
 #define HHSR_BM(TS, NT)                                                                                      \
     do {                                                                                                     \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(bm_l2_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        static std::atomic<unsigned long long> done{0};                                                      \
+        if (smem > 48 * 1024) ensure_dynamic_smem(bm_l2_kernel<TS>, done, smem);                              \
         bm_l2_kernel<TS><<<grid, NT, smem, st>>>(ref, ref_w, mov, mov_h, mov_w, F2, nx, radius);              \
     } while (0)
     if (ts == 32 && radius >= 1 && radius <= 4) {
@@ -477,7 +491,8 @@ extern "C" int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const f
     do {                                                                                                              \
         constexpr int N = 2 * R + 1, SW = 32 + 2 * R;                                                                 \
         const size_t sm = (size_t)(SW * SW + 8 * N * 3 * 33 + 8 * N * N + N * N) * sizeof(double);                    \
-        cudaFuncSetAttribute(bm_l2_tiled32_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);          \
+        static std::atomic<unsigned long long> done{0};                                                               \
+        ensure_dynamic_smem(bm_l2_tiled32_kernel<R>, done, sm);                                                       \
         bm_l2_tiled32_kernel<R><<<grid, 256, sm, st>>>(ref, ref_w, mov, mov_h, mov_w, F2, nx);                         \
     } while (0)
         switch (radius) {

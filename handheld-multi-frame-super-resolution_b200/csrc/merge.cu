@@ -13,13 +13,12 @@
 //   accumulate_pow2_kernel  scales 1, 2, 4 (the benchmark path): exact float32 position split, no float64; the
 //                           accumulators are updated by fire-and-forget 16-byte L2 reductions (never loaded by the SM);
 //   accumulate_kernel       any scale: the reference's float64 position per pixel, float4 load/add/store;
-//   accumulate_batch_kernel K frames per pass over the accumulators;
+//   accumulate_pow2_batch_kernel / accumulate_batch_kernel   several frames per pass over the accumulators, sums in registers;
 //   accumulate_ref_kernel   the reference frame (+ fused divide, + the frame-sharded peer sum, hhsr_reduce_merge_ref).
 // All of them share the per-pixel device functions below and the update  acc <- add.ftz(acc, r * sum)  and are
 // bit-equal where their domains overlap (tests/test_gpu_parity.py).  Compiled with -fmad=false (csrc/Makefile): every
 // fused multiply-add in this file is written explicitly, so the kernels round identically whatever the inlining.
 #include "common.cuh"
-#include <cstdlib>
 
 // resident CTAs per SM the register allocator must allow (measured optimum, profiles/merge_accumulate_r01_ncu.md)
 #ifndef HHSR_MERGE_MINBLOCKS
@@ -433,30 +432,15 @@ __device__ __forceinline__ void resolve_rggb(bool sy, bool sx, const float (&v)[
     out[0] = R, out[1] = G, out[2] = B;
 }
 
-template <bool ISO, int K, bool STORE>
-__global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_kernel(const __grid_constant__ MergeFrame f,
-                                                                                     const __grid_constant__ MergeGeom g,
-                                                                                     float *__restrict__ num,
-                                                                                     float *__restrict__ den) {
+// One comp frame, the four pixels of a thread.  `sink.pixel(p, r, val, acc)` receives the unscaled channel sums of pixel p
+// and its robustness; returns false (nothing emitted) when the thread has to take the generic per-pixel code: a 3x3
+// window touching the frame border or leaving the frame, or a CFA that is not a green-is-1 Bayer pattern.
+template <bool ISO, int K, class Sink>
+__device__ __forceinline__ bool pow2_frame(const MergeFrame &f, const MergeGeom &g, int by, float qy, int bx0, int tile, Sink &sink) {
     constexpr int SH = K + 1, MASK = (1 << SH) - 1;
     constexpr float INV = 1.0f / (float)(1 << SH);
-    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
-    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (hr_i >= g.Hs || j0 >= g.Ws) return;
-    const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
-    if (!STORE && (threadIdx.x & 1) == 0) {   // pre-touch the lines the L2 reductions will hit
-        prefetch_l2(num + base);
-        prefetch_l2(den + base);
-        prefetch_l2(num + base + 23);
-        prefetch_l2(den + base + 23);
-    }
     const int W = g.W, cw = g.cw;
-    // y split (shared by the four pixels)
-    const int n2 = 2 * hr_i + 1;
-    const int by = n2 >> SH;                                   // int(lr_y) <= H - 1
-    const float qy = (float)(n2 & MASK) * INV;
-    const int bx0 = j0 >> K;                                   // int(lr_x) of pixel 0; all four pixels lie in one tile
-    const float2 fl = __ldg(reinterpret_cast<const float2 *>(f.flow) + ((by >> g.ts_shift) * g.nx + (bx0 >> g.ts_shift)));
+    const float2 fl = __ldg(reinterpret_cast<const float2 *>(f.flow) + tile);
     const float fiy = truncf(fl.y), fix = truncf(fl.x);
     const float ffy = fl.y - fiy, ffx = fl.x - fix;
     int ly;
@@ -475,10 +459,7 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow
         cj[p] = bx + bp + lx;
     }
     // every 3x3 window strictly inside the frame (cj is non-decreasing in p) and a green-is-1 Bayer pattern?
-    if (!(ci >= 1 && ci <= g.H - 2 && cj[0] >= 1 && cj[3] <= W - 2 && g.cfa.bayer && g.cfa.dup == 1)) {
-        accumulate_thread_border<ISO, STORE>(&f, &g, num, den, hr_i, j0);
-        return;
-    }
+    if (!(ci >= 1 && ci <= g.H - 2 && cj[0] >= 1 && cj[3] <= W - 2 && g.cfa.bayer && g.cfa.dup == 1)) return false;
     // RGGB phase of the pattern: (py0, px0) = position of channel 0 ... pattern(y, x) = RGGB(y + py0, x + px0)
     const int red_at = ((g.cfa.packed & 3) == 0) ? 0 : (((g.cfa.packed >> 2) & 3) == 0) ? 1 : (((g.cfa.packed >> 4) & 3) == 0) ? 2 : 3;
     const bool sy = ((ci + (red_at >> 1)) & 1) != 0;
@@ -503,7 +484,6 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow
 #pragma unroll
         for (int c = 2; c < NCOL; ++c) col[c] = (c <= dmax + 1) ? cov_column(__ldg(q0 + c), __ldg(q1 + c), fry) : col[c - 1];
     }
-    float n[12], d[12], rr[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int bp = (2 * p + 1) >> SH;
@@ -521,44 +501,89 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow
         }
         float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, a[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
         merge_taps_off(f.raw, W, orow + cj[p], tx[p], ty, qxx, qxy, qyy, v, a);
-        rr[p] = __ldg(rrow + bp);
+        const float rp = __ldg(rrow + bp);
         const bool sx = ((cj[p] + px0) & 1) != 0;
         float val[3], acc[3];
         resolve_rggb(sy, sx, v, val);
         resolve_rggb(sy, sx, a, acc);
+        sink.pixel(p, rp, val, acc);
+    }
+    return true;
+}
+
+// Sink of the single-frame kernel: float4 number p-1 of the 12-float slice is complete after pixel p and leaves as one
+// 16-byte L2 reduction (or store) per accumulator.
+template <bool STORE>
+struct RedSink {
+    float *num, *den;      // this thread's slices
+    float n[12], d[12], rr[4];
+    __device__ __forceinline__ void pixel(int p, float r, const float (&val)[3], const float (&acc)[3]) {
+        rr[p] = r;
 #pragma unroll
         for (int c = 0; c < 3; ++c) n[3 * p + c] = val[c], d[3 * p + c] = acc[c];
-        if (p >= 1) {   // float4 number p-1 of the 12-float slice is complete
+        if (p >= 1) {
             const int q = p - 1;
-            rmw4<STORE>(num + base + 4 * q, rr[(4 * q) / 3], n[4 * q], rr[(4 * q + 1) / 3], n[4 * q + 1], rr[(4 * q + 2) / 3],
-                 n[4 * q + 2], rr[(4 * q + 3) / 3], n[4 * q + 3]);
-            rmw4<STORE>(den + base + 4 * q, rr[(4 * q) / 3], d[4 * q], rr[(4 * q + 1) / 3], d[4 * q + 1], rr[(4 * q + 2) / 3],
-                 d[4 * q + 2], rr[(4 * q + 3) / 3], d[4 * q + 3]);
+            rmw4<STORE>(num + 4 * q, rr[(4 * q) / 3], n[4 * q], rr[(4 * q + 1) / 3], n[4 * q + 1], rr[(4 * q + 2) / 3], n[4 * q + 2],
+                        rr[(4 * q + 3) / 3], n[4 * q + 3]);
+            rmw4<STORE>(den + 4 * q, rr[(4 * q) / 3], d[4 * q], rr[(4 * q + 1) / 3], d[4 * q + 1], rr[(4 * q + 2) / 3], d[4 * q + 2],
+                        rr[(4 * q + 3) / 3], d[4 * q + 3]);
         }
     }
+};
+
+template <bool ISO, int K, bool STORE>
+__global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_kernel(const __grid_constant__ MergeFrame f,
+                                                                                     const __grid_constant__ MergeGeom g,
+                                                                                     float *__restrict__ num,
+                                                                                     float *__restrict__ den) {
+    constexpr int SH = K + 1, MASK = (1 << SH) - 1;
+    constexpr float INV = 1.0f / (float)(1 << SH);
+    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (hr_i >= g.Hs || j0 >= g.Ws) return;
+    const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
+    if (!STORE && (threadIdx.x & 1) == 0) {   // pre-touch the lines the L2 reductions will hit
+        prefetch_l2(num + base);
+        prefetch_l2(den + base);
+        prefetch_l2(num + base + 23);
+        prefetch_l2(den + base + 23);
+    }
+    // y split (shared by the four pixels)
+    const int n2 = 2 * hr_i + 1;
+    const int by = n2 >> SH;                                   // int(lr_y) <= H - 1
+    const float qy = (float)(n2 & MASK) * INV;
+    const int bx0 = j0 >> K;                                   // int(lr_x) of pixel 0; all four pixels lie in one tile
+    RedSink<STORE> sink;
+    sink.num = num + base, sink.den = den + base;
+    if (!pow2_frame<ISO, K>(f, g, by, qy, bx0, (by >> g.ts_shift) * g.nx + (bx0 >> g.ts_shift), sink))
+        accumulate_thread_border<ISO, STORE>(&f, &g, num, den, hr_i, j0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// EXPERIMENT (HHSR_MERGE_BULK=1): same arithmetic as accumulate_pow2_kernel, but the accumulators are updated by the
-// TMA engine.  A warp owns 128 consecutive HR pixels of a row = 1536 contiguous bytes of each accumulator; its threads
-// park their products r * sum in shared memory and lane 0 issues ONE bulk asynchronous reduction per accumulator
-// (cp.reduce.async.bulk.global.shared::cta.add.f32, or a bulk store for the initialising first frame), so the SM issues
-// 2 bulk operations per warp instead of 192 16-byte reductions and the L2 receives whole 128-byte lines.
+// Frame-batched fast path: B comp frames in ONE pass over the accumulators.  The thread keeps its 2 x 12 accumulator
+// floats in registers (loaded once, or zero for the initialising batch), adds the frames in list order with the same
+// flush-to-zero addition as the L2 reduction of the single-frame kernel (bit-identical to B single-frame launches),
+// and stores the slice once: accumulator traffic per frame falls from 48 to 48/B (24/B) bytes per HR pixel, which
+// moves the merge from the HBM roofline to the instruction-issue limit of the tap arithmetic.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_reduce_add_f32(float *gdst, const float *ssrc, unsigned bytes) {
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
-                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_store(float *gdst, const float *ssrc, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-                 : "memory");
-}
+#ifndef HHSR_MERGE_BATCH_MINBLOCKS
+#define HHSR_MERGE_BATCH_MINBLOCKS 3
+#endif
+struct AddSink {
+    float n[12], d[12];
+    __device__ __forceinline__ void pixel(int p, float r, const float (&val)[3], const float (&acc)[3]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            n[3 * p + c] = add_ftz(n[3 * p + c], r, val[c]);
+            d[3 * p + c] = add_ftz(d[3 * p + c], r, acc[c]);
+        }
+    }
+};
 
-// border / generic threads of the bulk kernel: products of the four pixels straight into the warp's staging rows
-template <bool ISO, bool STORE>
-__device__ __noinline__ void border_products_to_smem(const MergeFrame *f, const MergeGeom *g, int hr_i, int j0, float *sn, float *sd) {
+// border threads of the batched kernel: unscaled sums and robustness of the four pixels of one frame through the generic
+// per-pixel code, into a scratch array (kept out of line so that the register accumulators never have their address taken)
+template <bool ISO>
+__device__ __noinline__ void border_frame_sums(const MergeFrame *f, const MergeGeom *g, int hr_i, int j0, float *out) {
     RowCtx rc;
     rc.lr_y = lr_coord(hr_i, g->scale, g->inv_scale, g->pow2);
     const int ily = (int)rc.lr_y;
@@ -568,147 +593,74 @@ __device__ __noinline__ void border_products_to_smem(const MergeFrame *f, const 
     cq.fx0 = cq.fy0 = -1;
     for (int p = 0; p < 4; ++p) {
         float val[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
-        const float r = (j0 + p < g->Ws) ? merge_hr_pixel<ISO>(*f, *g, j0 + p, rc, cq, val, acc) : 0.0f;
-        for (int c = 0; c < 3; ++c) {
-            sn[3 * p + c] = STORE ? add_ftz(0.f, r, val[c]) : r * val[c];
-            sd[3 * p + c] = STORE ? add_ftz(0.f, r, acc[c]) : r * acc[c];
-        }
+        out[24 + p] = (j0 + p < g->Ws) ? merge_hr_pixel<ISO>(*f, *g, j0 + p, rc, cq, val, acc) : 0.0f;
+        for (int c = 0; c < 3; ++c) out[3 * p + c] = val[c], out[12 + 3 * p + c] = acc[c];
     }
 }
 
 template <bool ISO, int K, bool STORE>
-__global__ void __launch_bounds__(256, HHSR_MERGE_POW2_MINBLOCKS) accumulate_pow2_bulk_kernel(const __grid_constant__ MergeFrame f,
-                                                                                          const __grid_constant__ MergeGeom g,
-                                                                                          float *__restrict__ num,
-                                                                                          float *__restrict__ den) {
+__global__ void __launch_bounds__(256, HHSR_MERGE_BATCH_MINBLOCKS) accumulate_pow2_batch_kernel(const __grid_constant__ MergeBatch b,
+                                                                                            const __grid_constant__ MergeGeom g,
+                                                                                            float *__restrict__ num,
+                                                                                            float *__restrict__ den) {
     constexpr int SH = K + 1, MASK = (1 << SH) - 1;
     constexpr float INV = 1.0f / (float)(1 << SH);
-    __shared__ __align__(128) float s_n[8][384];
-    __shared__ __align__(128) float s_d[8][384];
-    const int warp = threadIdx.y, lane = threadIdx.x;
-    const int hr_i = blockIdx.y * 8 + warp;
-    const int jw = blockIdx.x * 128, j0 = jw + lane * 4;
-    if (hr_i >= g.Hs) return;                       // warp-uniform
-    const bool active = j0 < g.Ws;
+    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (hr_i >= g.Hs || j0 >= g.Ws) return;
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
-    float *sn = &s_n[warp][lane * 12], *sd = &s_d[warp][lane * 12];
-    if (active) {
-        if (!STORE && (lane & 1) == 0) {
-            prefetch_l2(num + base);
-            prefetch_l2(den + base);
-            prefetch_l2(num + base + 23);
-            prefetch_l2(den + base + 23);
+    AddSink sink;
+    if (STORE) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) sink.n[q] = sink.d[q] = 0.f;
+    } else {   // issued first: in flight during the first frame's window arithmetic
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float4 a = *reinterpret_cast<const float4 *>(num + base + 4 * q);
+            const float4 c = *reinterpret_cast<const float4 *>(den + base + 4 * q);
+            sink.n[4 * q] = a.x, sink.n[4 * q + 1] = a.y, sink.n[4 * q + 2] = a.z, sink.n[4 * q + 3] = a.w;
+            sink.d[4 * q] = c.x, sink.d[4 * q + 1] = c.y, sink.d[4 * q + 2] = c.z, sink.d[4 * q + 3] = c.w;
         }
-        const int W = g.W, cw = g.cw;
-        const int n2 = 2 * hr_i + 1;
-        const int by = n2 >> SH;
-        const float qy = (float)(n2 & MASK) * INV;
-        const int bx0 = j0 >> K;
-        const float2 fl = __ldg(reinterpret_cast<const float2 *>(f.flow) + ((by >> g.ts_shift) * g.nx + (bx0 >> g.ts_shift)));
-        const float fiy = truncf(fl.y), fix = truncf(fl.x);
-        const float ffy = fl.y - fiy, ffx = fl.x - fix;
-        int ly;
-        float ty;
-        split_q(qy, ffy, ly, ty);
-        const int ci = by + (int)fiy + ly;
-        const int bx = bx0 + (int)fix;
-        int cj[4];
-        float tx[4];
+    }
+    const int n2 = 2 * hr_i + 1;
+    const int by = n2 >> SH;
+    const float qy = (float)(n2 & MASK) * INV;
+    const int bx0 = j0 >> K;
+    const int tile = (by >> g.ts_shift) * g.nx + (bx0 >> g.ts_shift);
+#pragma unroll 1
+    for (int k = 0; k < b.K; ++k) {
+        if (!pow2_frame<ISO, K>(b.f[k], g, by, qy, bx0, tile, sink)) {
+            float tmp[28];
+            border_frame_sums<ISO>(&b.f[k], &g, hr_i, j0, tmp);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int bp = (2 * p + 1) >> SH;
-            const float qp = (float)((2 * p + 1) & MASK) * INV;
-            int lx;
-            split_q(qp, ffx, lx, tx[p]);
-            cj[p] = bx + bp + lx;
-        }
-        if (!(ci >= 1 && ci <= g.H - 2 && cj[0] >= 1 && cj[3] <= W - 2 && g.cfa.bayer && g.cfa.dup == 1)) {
-            border_products_to_smem<ISO, STORE>(&f, &g, hr_i, j0, sn, sd);
-        } else {
-            const int red_at = ((g.cfa.packed & 3) == 0) ? 0 : (((g.cfa.packed >> 2) & 3) == 0) ? 1 : (((g.cfa.packed >> 4) & 3) == 0) ? 2 : 3;
-            const bool sy = ((ci + (red_at >> 1)) & 1) != 0;
-            const int px0 = red_at & 1;
-            const int orow = ci * W;
-            const float *rrow = f.r + (by * W + bx0);
-            const int oqy = ((ci - 1) >> 1) * cw;
-            const float fry = fmaf(0.5f, ty, (ci & 1) ? 0.0f : 0.5f);
-            constexpr int NCOL = (K == 0) ? 4 : 3;
-            CovCol col[NCOL];
-            const int i0 = (cj[0] - 1) >> 1;
-            if (!ISO) {
-                const float4 *q0 = reinterpret_cast<const float4 *>(f.covs) + (oqy + i0);
-                const float4 *q1 = q0 + cw;
-                const int dmax = ((cj[3] - 1) >> 1) - i0;
-                col[0] = cov_column(__ldg(q0), __ldg(q1), fry);
-                col[1] = cov_column(__ldg(q0 + 1), __ldg(q1 + 1), fry);
-#pragma unroll
-                for (int c = 2; c < NCOL; ++c) col[c] = (c <= dmax + 1) ? cov_column(__ldg(q0 + c), __ldg(q1 + c), fry) : col[c - 1];
-            }
-            float n[12], d[12];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int bp = (2 * p + 1) >> SH;
-                float qxx, qxy, qyy;
-                if (ISO) {
-                    qxx = qyy = 2.0f * -0.72134752044448170368f, qxy = 0.0f;
-                } else {
-                    const int dcol = ((cj[p] - 1) >> 1) - i0;
-                    const float frx = fmaf(0.5f, tx[p], (cj[p] & 1) ? 0.0f : 0.5f);
-                    CovCol l = col[0], r = col[1];
-#pragma unroll
-                    for (int c = 1; c < NCOL - 1; ++c)
-                        if (dcol == c) l = col[c], r = col[c + 1];
-                    cov_form_cols(l, r, frx, qxx, qxy, qyy);
-                }
-                float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, a[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-                merge_taps_off(f.raw, W, orow + cj[p], tx[p], ty, qxx, qxy, qyy, v, a);
-                const float rp = __ldg(rrow + bp);
-                const bool sx = ((cj[p] + px0) & 1) != 0;
-                float val[3], acc[3];
-                resolve_rggb(sy, sx, v, val);
-                resolve_rggb(sy, sx, a, acc);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    n[3 * p + c] = STORE ? add_ftz(0.f, rp, val[c]) : rp * val[c];
-                    d[3 * p + c] = STORE ? add_ftz(0.f, rp, acc[c]) : rp * acc[c];
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                *reinterpret_cast<float4 *>(sn + 4 * q) = make_float4(n[4 * q], n[4 * q + 1], n[4 * q + 2], n[4 * q + 3]);
-                *reinterpret_cast<float4 *>(sd + 4 * q) = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+            for (int q = 0; q < 12; ++q) {
+                sink.n[q] = add_ftz(sink.n[q], tmp[24 + q / 3], tmp[q]);
+                sink.d[q] = add_ftz(sink.d[q], tmp[24 + q / 3], tmp[12 + q]);
             }
         }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk engine
-    __syncwarp();
-    if (lane == 0) {
-        const unsigned bytes = (unsigned)min(128, g.Ws - jw) * 12u;
-        float *gn = num + ((size_t)hr_i * g.Ws + jw) * 3, *gd = den + ((size_t)hr_i * g.Ws + jw) * 3;
-        if (STORE) {
-            bulk_store(gn, s_n[warp], bytes);
-            bulk_store(gd, s_d[warp], bytes);
-        } else {
-            bulk_reduce_add_f32(gn, s_n[warp], bytes);
-            bulk_reduce_add_f32(gd, s_d[warp], bytes);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging rows stay valid until they have been read
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        *reinterpret_cast<float4 *>(num + base + 4 * q) = make_float4(sink.n[4 * q], sink.n[4 * q + 1], sink.n[4 * q + 2], sink.n[4 * q + 3]);
+        *reinterpret_cast<float4 *>(den + base + 4 * q) = make_float4(sink.d[4 * q], sink.d[4 * q + 1], sink.d[4 * q + 2], sink.d[4 * q + 3]);
     }
 }
 
 // K comp frames in one pass over the accumulators (B200 addition).  The slice is loaded first and the frames are
 // added in list order, so the result is bit-identical to K single-frame launches.
-template <bool ISO, int VEC>
-__global__ void __launch_bounds__(256, 2) accumulate_batch_kernel(MergeBatch b, MergeGeom g, float *__restrict__ num,
-                                                                  float *__restrict__ den) {
+template <bool ISO, int VEC, bool STORE>
+__global__ void __launch_bounds__(256, 2) accumulate_batch_kernel(const __grid_constant__ MergeBatch b, const __grid_constant__ MergeGeom g,
+                                                                  float *__restrict__ num, float *__restrict__ den) {
     const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (hr_i >= g.Hs || j0 >= g.Ws) return;
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
     const bool full = (VEC == 4) && (j0 + VEC <= g.Ws);
     float n[VEC * 3], d[VEC * 3];
-    if (full) {
+    if (STORE) {
+#pragma unroll
+        for (int q = 0; q < VEC * 3; ++q) n[q] = d[q] = 0.f;
+    } else if (full) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             const float4 a = *reinterpret_cast<const float4 *>(num + base + 4 * q);
@@ -1010,49 +962,46 @@ static void launch_accumulate_vec(const MergeBatch &b, const MergeGeom &g, float
             accumulate_kernel<false, VEC, STORE><<<grid, block, 0, st>>>(b.f[0], g, num, den);
     } else {
         if (iso)
-            accumulate_batch_kernel<true, VEC><<<grid, block, 0, st>>>(b, g, num, den);
+            accumulate_batch_kernel<true, VEC, STORE><<<grid, block, 0, st>>>(b, g, num, den);
         else
-            accumulate_batch_kernel<false, VEC><<<grid, block, 0, st>>>(b, g, num, den);
+            accumulate_batch_kernel<false, VEC, STORE><<<grid, block, 0, st>>>(b, g, num, den);
     }
 }
 
-// scale 1, 2 or 4 with the geometry the fast path assumes; HHSR_MERGE_GENERIC=1 forces the generic kernel (A/B tests)
+// scale 1, 2 or 4 with the geometry the fast path assumes (-1: the any-scale kernel has to run)
 static int pow2_fast_shift(const MergeGeom &g) {
-    const char *e = std::getenv("HHSR_MERGE_GENERIC");
-    const bool force_generic = e && e[0] == '1';
-    if (force_generic || !g.pow2 || g.ts_shift < 2 || g.Ws % 4 != 0) return -1;
+    if (!g.pow2 || g.ts_shift < 2 || g.Ws % 4 != 0) return -1;
     for (int k = 0; k <= 2; ++k)
         if (g.scale == (double)(1 << k) && g.Hs == (g.H << k) && g.Ws == (g.W << k)) return k;
     return -1;
 }
 
 template <int K, bool STORE>
-static void launch_pow2(const MergeFrame &f, const MergeGeom &g, float *num, float *den, int iso, dim3 grid, dim3 block,
+static void launch_pow2(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso, dim3 grid, dim3 block,
                         cudaStream_t st) {
-    const char *e = std::getenv("HHSR_MERGE_BULK");
-    if (e && e[0] == '1') {      // experiment: accumulator traffic through the TMA engine (see accumulate_pow2_bulk_kernel)
+    if (b.K == 1) {
         if (iso)
-            accumulate_pow2_bulk_kernel<true, K, STORE><<<grid, block, 0, st>>>(f, g, num, den);
+            accumulate_pow2_kernel<true, K, STORE><<<grid, block, 0, st>>>(b.f[0], g, num, den);
         else
-            accumulate_pow2_bulk_kernel<false, K, STORE><<<grid, block, 0, st>>>(f, g, num, den);
-        return;
+            accumulate_pow2_kernel<false, K, STORE><<<grid, block, 0, st>>>(b.f[0], g, num, den);
+    } else {
+        if (iso)
+            accumulate_pow2_batch_kernel<true, K, STORE><<<grid, block, 0, st>>>(b, g, num, den);
+        else
+            accumulate_pow2_batch_kernel<false, K, STORE><<<grid, block, 0, st>>>(b, g, num, den);
     }
-    if (iso)
-        accumulate_pow2_kernel<true, K, STORE><<<grid, block, 0, st>>>(f, g, num, den);
-    else
-        accumulate_pow2_kernel<false, K, STORE><<<grid, block, 0, st>>>(f, g, num, den);
 }
 
 template <bool STORE>
-static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso,
+static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso, bool generic,
                              cudaStream_t st) {
     dim3 block(32, 8);
-    const int k = b.K == 1 ? pow2_fast_shift(g) : -1;
+    const int k = generic ? -1 : pow2_fast_shift(g);
     if (k >= 0) {
         dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8));
-        if (k == 0) launch_pow2<0, STORE>(b.f[0], g, num, den, iso, grid, block, st);
-        if (k == 1) launch_pow2<1, STORE>(b.f[0], g, num, den, iso, grid, block, st);
-        if (k == 2) launch_pow2<2, STORE>(b.f[0], g, num, den, iso, grid, block, st);
+        if (k == 0) launch_pow2<0, STORE>(b, g, num, den, iso, grid, block, st);
+        if (k == 1) launch_pow2<1, STORE>(b, g, num, den, iso, grid, block, st);
+        if (k == 2) launch_pow2<2, STORE>(b, g, num, den, iso, grid, block, st);
         return launch_status("merge_accumulate");
     }
     if (g.Ws % 4 == 0)
@@ -1068,7 +1017,9 @@ using namespace hhsr;
 
 static int merge_frames(const float *const *raws, const float *const *flows, const float *const *covs, const float *const *rs,
                         int K, int H, int W, int ny, int nx, int ts, float *num, float *den, int Hs, int Ws, double scale,
-                        const int *cfa_host, int iso, bool store, hhsr_stream_t stream) {
+                        const int *cfa_host, int iso, int flags, hhsr_stream_t stream) {
+    HHSR_REQUIRE((flags & ~(HHSR_MERGE_INIT | HHSR_MERGE_GENERIC)) == 0, "unknown merge flag");
+    const bool generic = (flags & HHSR_MERGE_GENERIC) != 0;
     HHSR_REQUIRE(raws && flows && rs && K > 0, "null frame list");
     HHSR_REQUIRE(iso || covs, "covs required for the steerable kernel");
     if (int e = check_merge_args(raws[0], num, den, H, W, Hs, Ws, scale, cfa_host)) return e;
@@ -1082,8 +1033,10 @@ static int merge_frames(const float *const *raws, const float *const *flows, con
             HHSR_REQUIRE(iso || ((uintptr_t)covs[k0 + k] % 16 == 0 && covs[k0 + k]), "covs must be 16-byte aligned");
             b.f[k] = MergeFrame{raws[k0 + k], flows[k0 + k], iso ? nullptr : covs[k0 + k], rs[k0 + k]};
         }
-        const int e = store ? launch_accumulate<true>(b, g, num, den, iso, (cudaStream_t)stream)
-                            : launch_accumulate<false>(b, g, num, den, iso, (cudaStream_t)stream);
+        // only the first chunk of an initialising call stores; later chunks accumulate onto it
+        const bool store = (flags & HHSR_MERGE_INIT) != 0 && k0 == 0;
+        const int e = store ? launch_accumulate<true>(b, g, num, den, iso, generic, (cudaStream_t)stream)
+                            : launch_accumulate<false>(b, g, num, den, iso, generic, (cudaStream_t)stream);
         if (e) return e;
     }
     return 0;
@@ -1092,20 +1045,20 @@ static int merge_frames(const float *const *raws, const float *const *flows, con
 extern "C" int hhsr_merge_accumulate_batch(const float *const *raws, const float *const *flows,
                                            const float *const *covs, const float *const *rs, int K, int H, int W,
                                            int ny, int nx, int ts, float *num, float *den, int Hs, int Ws,
-                                           double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
-    return merge_frames(raws, flows, covs, rs, K, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, false, stream);
+                                           double scale, const int *cfa_host, int iso, int flags, hhsr_stream_t stream) {
+    return merge_frames(raws, flows, covs, rs, K, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, flags, stream);
 }
 
 extern "C" int hhsr_merge_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
                                      const float *covs, const float *r, float *num, float *den, int Hs, int Ws,
                                      double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
-    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, false, stream);
+    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, 0, stream);
 }
 
 extern "C" int hhsr_merge_init_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
                                           const float *covs, const float *r, float *num, float *den, int Hs, int Ws,
                                           double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
-    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, true, stream);
+    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, HHSR_MERGE_INIT, stream);
 }
 
 static int launch_merge_ref(const float *raw, const float *covs, const MergeGeom &g, float *num, float *den, int iso,

@@ -10,7 +10,6 @@
 // Arithmetic follows the compiled reference: float64 wherever Numba promotes (white-balance division, Dodgson
 // weights, noise-model shrinkage, the final S*exp - t), float32 sums where the reference keeps float32 arrays.
 #include "common.cuh"
-#include <cstdlib>
 
 namespace hhsr {
 
@@ -736,14 +735,14 @@ extern "C" int hhsr_ref_stats_terms(const float *guide_means, const float *guide
 
 extern "C" int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_terms, int H, int W,
                                const float *flow, int ny, int nx, int ts, double t, double s1, double s2, double Mt,
-                               float *R, hhsr_stream_t stream) {
+                               float *R, int flags, hhsr_stream_t stream) {
     HHSR_REQUIRE(comp_means_lr && ref_means && ref_terms && flow && R, "null pointer");
+    HHSR_REQUIRE((flags & ~HHSR_ROBUSTNESS_GENERIC) == 0, "unknown robustness flag");
     HHSR_REQUIRE(H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "frame sides must be even");
     HHSR_REQUIRE(ts > 0 && ny * ts >= H && nx * ts >= W, "flow grid does not cover the frame");
     HHSR_REQUIRE((uintptr_t)ref_means % 16 == 0 && (uintptr_t)ref_terms % 16 == 0 && (uintptr_t)R % 16 == 0,
                  "ref_means / ref_terms / R must be 16-byte aligned");
-    const char *e = std::getenv("HHSR_ROBUSTNESS_GENERIC");     // A/B tests: force the per-pixel path
-    RobParams p{t, s1, s2, Mt, (e && e[0] == '1') ? 1 : 0};
+    RobParams p{t, s1, s2, Mt, (flags & HHSR_ROBUSTNESS_GENERIC) ? 1 : 0};
     dim3 block(RTX, RTY), grid(ceil_div(W, RTX * 4), ceil_div(H, RTY * 2));
     robustness_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(comp_means_lr, ref_means, ref_terms, H, W, flow, ny, nx, ts, p, R);
     return launch_status("robustness");

@@ -36,12 +36,12 @@ SIGNATURES = {
     "hhsr_noise_table": [_P, _P, _I, _P, _P],
     "hhsr_ref_stats_terms": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P],
     "hhsr_robustness_ref_terms": [_P, _P, _I, _I, _P, _I, _P, _P],
-    "hhsr_robustness": [_P, _P, _P, _I, _I, _P, _I, _I, _I, _D, _D, _D, _D, _P, _P],
+    "hhsr_robustness": [_P, _P, _P, _I, _I, _P, _I, _I, _I, _D, _D, _D, _D, _P, _I, _P],
     "hhsr_local_min5": [_P, _I, _I, _P, _P, _P],
     "hhsr_merge_accumulate": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _D, _IP, _I, _P],
     "hhsr_merge_init_accumulate": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _D, _IP, _I, _P],
     "hhsr_merge_accumulate_batch": [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _I,
-                                    _I, _P, _P, _I, _I, _D, _IP, _I, _P],
+                                    _I, _P, _P, _I, _I, _D, _IP, _I, _I, _P],
     "hhsr_merge_ref": [_P, _I, _I, _P, _P, _P, _I, _I, _D, _IP, _I, _P, _I, _I, _D, _I, _I, _I, _P],
     "hhsr_normalize_raw_u16": [_P, _I, _I, _FP, _FP, _FP, _P, _P],
     "hhsr_reduce_merge_ref": [C.POINTER(_P), C.POINTER(_P), _I, _P, _I, _I, _P, _P, _I, _I, _D, _IP, _I, _P, _I, _I, _D, _I,

@@ -30,9 +30,16 @@ def merge(comp_img, alignments, covs, r, num, den, cfa_pattern, config, init=Fal
               _lib.stream())
 
 
-def merge_batch(comp_imgs, alignments, covs, rs, num, den, cfa_pattern, config):
-    """Same arithmetic as calling merge() once per frame in list order, in ONE pass over num/den: the accumulators
-    are read and written once instead of once per frame (B200 addition, SURVEY section 8d "K-frame batched merge")."""
+MERGE_INIT, MERGE_GENERIC = 1, 2      # include/hhsr.h: HHSR_MERGE_INIT, HHSR_MERGE_GENERIC
+
+
+def merge_batch(comp_imgs, alignments, covs, rs, num, den, cfa_pattern, config, init=False, generic=False):
+    """Same arithmetic as calling merge() once per frame in list order (bit-identical), in ONE pass over num/den: the
+    accumulators are read and written once instead of once per frame (B200 addition, SURVEY section 8d "K-frame
+    batched merge").  init=True: the batch initialises num/den (their previous contents are ignored) — what main() does
+    with the first batch of a burst.  generic=True forces the any-scale kernel (A/B parity tests)."""
+    if config.mode != "bayer":
+        raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
     _check_acc(num, den)
     K = len(comp_imgs)
     H, W = comp_imgs[0].shape
@@ -41,7 +48,8 @@ def merge_batch(comp_imgs, alignments, covs, rs, num, den, cfa_pattern, config):
     arr = lambda ts: (C.c_void_p * K)(*[t.data_ptr() if t is not None else 0 for t in ts])  # noqa: E731
     _lib.call("hhsr_merge_accumulate_batch", arr(comp_imgs), arr(alignments), arr([None] * K if iso else covs), arr(rs),
               K, H, W, ny, nx, int(config.block_matching.tuning.tile_size), _lib.ptr(num), _lib.ptr(den), num.shape[0],
-              num.shape[1], float(config.scale), _lib.cfa_array(cfa_pattern), int(iso), _lib.stream())
+              num.shape[1], float(config.scale), _lib.cfa_array(cfa_pattern), int(iso),
+              (MERGE_INIT if init else 0) | (MERGE_GENERIC if generic else 0), _lib.stream())
 
 
 def merge_ref(ref_img, kernels, num, den, cfa_pattern, config, acc_rob=None, fuse_divide=False, rows=None):

@@ -125,11 +125,12 @@ def local_min(R, acc_rob=None):
 
 
 def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pattern, white_balance, noise_model,
-                       config, acc_rob=None, return_R=False):
+                       config, acc_rob=None, return_R=False, generic=False):
     """Robustness map r [H, W] of comp frame J_n (Alg. 6, robustness.py:79-170).  Three launches: guide statistics
     at half resolution, the fused per-pixel kernel (warp, distance, noise model, S, threshold), 5x5 minimum (plus,
     for the first comp frame of a burst, the reference-side noise terms).
-    `acc_rob` (float64 [H,W]), when given, is incremented by r in the last launch (super_resolution.py:159)."""
+    `acc_rob` (float64 [H,W]), when given, is incremented by r in the last launch (super_resolution.py:159);
+    generic=True forces the per-pixel path of the fused kernel (A/B parity tests)."""
     comp_img = _lib.as_device(comp_img)
     H, W = comp_img.shape
     if not config.robustness.enabled:
@@ -146,6 +147,6 @@ def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pat
     terms = ref_noise_terms(ref_local_means, ref_local_stds, table)
     _lib.call("hhsr_robustness", _lib.ptr(comp_means), _lib.ptr(ref_local_means), _lib.ptr(terms), H, W,
               _lib.ptr(flows), flows.shape[0], flows.shape[1], int(ts),
-              float(tun.t), float(tun.s1), float(tun.s2), float(tun.Mt), _lib.ptr(R), _lib.stream())
+              float(tun.t), float(tun.s1), float(tun.s2), float(tun.Mt), _lib.ptr(R), int(bool(generic)), _lib.stream())
     r = local_min(R, acc_rob)
     return (r, R) if return_R else r

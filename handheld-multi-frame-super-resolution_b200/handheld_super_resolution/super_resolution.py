@@ -8,7 +8,7 @@ import torch
 
 from .alignment import align, init_alignment
 from .kernels import estimate_kernels
-from .merge import merge, merge_ref
+from .merge import merge, merge_batch, merge_ref
 from .params import sanitize_config, update_snr_config
 from .robustness import compute_robustness, init_robustness
 from .utils import add_many, timer
@@ -49,6 +49,9 @@ def _align_stream(device, i=0):
 
 
 ALIGN_AHEAD = int(os.environ.get("HHSR_ALIGN_AHEAD", "1"))   # alignment chains in flight ahead of the merge (0: one stream)
+# comp frames merged per pass over the accumulators (merge_batch): their raw / flow / covariance / robustness arrays
+# stay resident (144 MB per 12 MP frame) until the batch is merged.  1 = the reference's one launch per frame.
+MERGE_BATCH = int(os.environ.get("HHSR_MERGE_BATCH", "24"))
 
 
 def _host_tensor(frame):
@@ -73,12 +76,14 @@ class FrameFeeder:
     compute stream, so the caching allocator serves them from the same pool every burst), one frame ahead of the
     compute stream; uint16 frames (sensor counts) cross PCIe as 2 bytes per pixel and are normalised on the device
     (utils_dng.RawNormalization, the reference's utils_dng.py:146-160).  CUDA float32 frames pass through."""
-    SLOTS = 2 + max(ALIGN_AHEAD, 1)      # frame being merged + frames being aligned + frame being uploaded
+    # frame being merged + frames being aligned + frame being uploaded (+ batch - 1 frames waiting in a merge batch)
+    SLOTS = int(os.environ.get("HHSR_STAGING_SLOTS", str(2 + max(ALIGN_AHEAD, 1))))
     _RINGS = {}     # (device, compute stream, role, shape, dtype, slot) -> [buffer, event "slot free"]: staging buffers live
                     # across bursts, so the first uploads of burst i+1 need not wait for the compute stream to drain burst i
 
-    def __init__(self, frames, ids, config, device, role="comp"):
+    def __init__(self, frames, ids, config, device, role="comp", extra_slots=0):
         self.frames, self.ids, self.config, self.device, self.role = frames, list(ids), config, device, role
+        self.SLOTS = FrameFeeder.SLOTS + extra_slots     # frames waiting in a merge batch keep their slots
         self.compute = torch.cuda.current_stream(device)
         self.copy = _copy_stream(device)
         self.norm = None
@@ -144,7 +149,7 @@ class FrameFeeder:
             item[2][1] = ev
 
 
-def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulators=None, finalize_fn=None):
+def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulators=None, finalize_fn=None, merge_batch_size=None):
     """Device pipeline (super_resolution.py:41-200).
 
     ref_img [H,W], comp_imgs [N-1,H,W]: float32 host arrays (numpy / pinned torch) or CUDA tensors.
@@ -154,7 +159,9 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     frames (frame sharding) and `reduce_fn(num, den, acc_rob)` is called once after the loop — the one natural
     reduction point of the pipeline.  `accumulators=(num, den)` supplies caller-owned accumulators
     (e.g. peer-mapped symmetric memory; zeroed here) and `finalize_fn(ref_img, covs, num, den, acc_rob, cfa, config)`
-    replaces reduction + merge_ref + divide by one fused step (distributed.P2PReduce) and returns the image."""
+    replaces reduction + merge_ref + divide by one fused step (distributed.P2PReduce) and returns the image.
+    `merge_batch_size` (default MERGE_BATCH): comp frames accumulated per pass over num/den (merge.merge_batch; the result
+    is bit-identical for every batch size)."""
     verbose_2 = config.verbose >= 2
     grey_method = config.grey_method
     if config.mode != "bayer":
@@ -165,6 +172,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     compute_robustness_ = timer(compute_robustness, verbose_2, "\nEstimating robustness", "Robustness estimated (Total)")
     estimate_kernels_ = timer(estimate_kernels, verbose_2, "\nEstimating kernels", "Kernels estimated (Total)")
     merge_ = timer(merge, verbose_2, "\nAccumulating Image", "Image accumulated (Total)")
+    merge_batch_ = timer(merge_batch, verbose_2, "\nAccumulating Image", "Image accumulated (Total)")
     merge_ref_ = timer(merge_ref, verbose_2, "\nAccumulating ref Img", "Ref Img accumulated (Total)")
 
     debug_mode = config.debug
@@ -209,8 +217,10 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     accumulated_r = torch.zeros((H, W), dtype=torch.float64, device=dev) if accumulate_r else None
 
     _mark("ref_side")
-    feed = FrameFeeder(comp_imgs, ids, config, dev)
-    r_maps = []
+    batch_size = max(1, int(MERGE_BATCH if merge_batch_size is None else merge_batch_size))
+    feed = FrameFeeder(comp_imgs, ids, config, dev, extra_slots=batch_size - 1)
+    pending = []        # (k, frame, flow, covs, r) of the frames waiting for the next pass over the accumulators
+    merged_any = False
     main_stream = torch.cuda.current_stream(dev)
     ahead = 0 if (os.environ.get("HHSR_SINGLE_STREAM", "0") == "1" or verbose_2) else ALIGN_AHEAD
 
@@ -246,17 +256,23 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
             debug_dict["flow"].append(flow.cpu().numpy())
         r = compute_robustness_(cuda_img, ref_local_means, ref_local_stds, flow, cfa_pattern, white_balance,
                                 noise_tab, config)
-        if accumulate_r:
-            r_maps.append(r)      # accumulated_r += r (super_resolution.py:159), summed in frame order after the loop
         covs = estimate_kernels_(cuda_img, config)
-        merge_(cuda_img, flow, covs, r, num, den, cfa_pattern, config, init=(k == 0))
-        feed.release(k)
+        pending.append((k, cuda_img, flow, covs, r))
+        if len(pending) == batch_size or k == len(ids) - 1:
+            # one pass over num/den for the whole batch; the first batch of a burst initialises them
+            if len(pending) == 1:
+                merge_(cuda_img, flow, covs, r, num, den, cfa_pattern, config, init=not merged_any)
+            else:
+                merge_batch_([p[1] for p in pending], [p[2] for p in pending], [p[3] for p in pending],
+                             [p[4] for p in pending], num, den, cfa_pattern, config, init=not merged_any)
+            merged_any = True
+            if accumulate_r:      # accumulated_r += r (super_resolution.py:159), in frame order, one pass per batch
+                add_many(accumulated_r, [p[4] for p in pending])
+            for p in pending:
+                feed.release(p[0])
+            pending = []
         if debug_mode:
             debug_dict["robustness"].append(r.cpu().numpy())
-
-    if accumulate_r:
-        add_many(accumulated_r, r_maps)
-        r_maps = []
 
     # the one reduction point of the pipeline (frame-sharded runs): reduce_fn sums the accumulators across ranks and
     # may hand back the slice of output rows this rank has to normalise plus a callable that re-assembles the image

@@ -121,10 +121,12 @@ int hhsr_ref_stats_terms(const float *guide_means, const float *guide_vars, int 
                          int n_curve, float *ref_means, float *ref_vars, float *terms, hhsr_stream_t stream);
 /* fused per-pixel robustness (robustness.py:421-639): warped Dodgson upsampling of the comp guide means,
  * |mean difference|, noise-model shrinkage, flow-irregularity factor S and threshold -> R [H][W].
- * ref_means: [3][H][W] from hhsr_upscale_warp_stats; ref_terms: [4][H][W] from hhsr_robustness_ref_terms. */
+ * ref_means: [3][H][W] from hhsr_upscale_warp_stats; ref_terms: [4][H][W] from hhsr_robustness_ref_terms.
+ * flags: HHSR_ROBUSTNESS_GENERIC forces the per-pixel path where the block-uniform fast path applies (A/B parity tests). */
+#define HHSR_ROBUSTNESS_GENERIC 1
 int hhsr_robustness(const float *comp_means_lr, const float *ref_means, const float *ref_terms, int H, int W,
                     const float *flow, int ny, int nx, int ts, double t, double s1, double s2, double Mt, float *R,
-                    hhsr_stream_t stream);
+                    int flags, hhsr_stream_t stream);
 /* 5x5 edge-replicated local minimum (robustness.py:641-687); when acc_rob != NULL also acc_rob += r
  * (utils.py:93-120, float64 accumulator). */
 int hhsr_local_min5(const float *R, int H, int W, float *r, double *acc_rob, hhsr_stream_t stream);
@@ -145,11 +147,16 @@ int hhsr_merge_accumulate(const float *raw, int H, int W, const float *flow, int
 int hhsr_merge_init_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
                                const float *covs, const float *r, float *num, float *den, int Hs, int Ws,
                                double scale, const int *cfa_host, int iso, hhsr_stream_t stream);
-/* Same arithmetic for K comp frames in one pass over the accumulators (frame order preserved per pixel).
- * raws/flows/covs/rs: HOST arrays of K device pointers. */
+/* Same arithmetic for K comp frames in ONE pass over the accumulators (B200 addition; frame order preserved per pixel,
+ * bit-identical to K single-frame calls): the accumulators are read and written once per call instead of once per
+ * frame.  raws/flows/covs/rs: HOST arrays of K device pointers.  flags: HHSR_MERGE_INIT — num/den are initialised by
+ * the batch (previous contents ignored) instead of updated; HHSR_MERGE_GENERIC — run the any-scale kernel even where
+ * the power-of-two fast path applies (A/B parity tests). */
+#define HHSR_MERGE_INIT 1
+#define HHSR_MERGE_GENERIC 2
 int hhsr_merge_accumulate_batch(const float *const *raws, const float *const *flows, const float *const *covs,
                                 const float *const *rs, int K, int H, int W, int ny, int nx, int ts, float *num,
-                                float *den, int Hs, int Ws, double scale, const int *cfa_host, int iso,
+                                float *den, int Hs, int Ws, double scale, const int *cfa_host, int iso, int flags,
                                 hhsr_stream_t stream);
 /* ---- merge of the reference frame, Alg. 11 (merge.py:22-233).  acc_rob (float64 [H][W]) may be NULL; when given,
  * the accumulated-robustness denoiser rules apply (widened window / overwrite).  fuse_divide != 0 additionally

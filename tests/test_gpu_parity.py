@@ -312,13 +312,8 @@ def test_robustness_tile_path_equals_pixel_path():
     flow[7, 8] = torch.tensor([2.0, -3.0], device="cuda")
     flow[0, 0] = torch.tensor([-70.0, 1.0], device="cuda")     # leaves the frame
     outs = []
-    for generic in ("1", "0"):
-        os.environ["HHSR_ROBUSTNESS_GENERIC"] = generic
-        try:
-            r, R = RB.compute_robustness(burst[1], m, s, flow, CFA, WB, (std, diff), cfg, return_R=True)
-            torch.cuda.synchronize()
-        finally:
-            os.environ.pop("HHSR_ROBUSTNESS_GENERIC", None)
+    for generic in (True, False):
+        r, R = RB.compute_robustness(burst[1], m, s, flow, CFA, WB, (std, diff), cfg, return_R=True, generic=generic)
         outs.append(R)
     d = (outs[0] - outs[1]).abs()
     record("robustness_tile_vs_pixel", float(d.max()))
@@ -433,49 +428,30 @@ def test_merge_pow2_fast_path_equals_generic(scale, cfa):
     for kern in ("steerable", "iso"):
         cfg = attr_cfg(scale=scale, kernel=kern)
         outs = []
-        for generic in ("1", "0"):
-            os.environ["HHSR_MERGE_GENERIC"] = generic
-            try:
-                num = torch.rand((scale * H, scale * W, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
-                den = num.clone() + 1.0
+        for generic in (True, False):
+            num = torch.rand((scale * H, scale * W, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+            den = num.clone() + 1.0
+            if generic:     # hhsr_merge_accumulate_batch with one frame and HHSR_MERGE_GENERIC
+                MG.merge_batch([raw], [flow], [covs], [r], num, den, cfa, cfg, generic=True)
+            else:
                 MG.merge(raw, flow, covs, r, num, den, cfa, cfg)
-                torch.cuda.synchronize()
-            finally:
-                os.environ.pop("HHSR_MERGE_GENERIC", None)
             outs.append((num, den))
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (scale, cfa, kern)
-
-
-@pytest.mark.parametrize("scale", [1, 2, 4])
-def test_merge_bulk_variant_equals_default(scale):
-    """HHSR_MERGE_BULK=1 (accumulators updated by bulk asynchronous reductions from shared memory — the TMA engine —
-    instead of per-thread 16-byte L2 reductions) must give the same accumulators as the default kernel, also for the
-    initialising first frame and for a width that leaves the last warp partly outside the image."""
-    from handheld_super_resolution import merge as MG
-    g = torch.Generator(device="cuda").manual_seed(40 + scale)
-    H, W, ts = 96, 208, 16          # W * scale is not a multiple of 128
-    raw = torch.rand((H, W), device="cuda", generator=g)
-    flow = (torch.rand((H // ts, W // ts, 2), device="cuda", generator=g) - 0.5) * 8.0
-    e = torch.rand((H // 2, W // 2, 3), device="cuda", generator=g)
-    k1, k2, th = 0.2 + 2.0 * e[..., 0], 0.2 + 2.0 * e[..., 1], 6.2832 * e[..., 2]
-    c, s_ = torch.cos(th), torch.sin(th)
-    covs = torch.stack([k1 * k1 * c * c + k2 * k2 * s_ * s_, (k1 * k1 - k2 * k2) * c * s_, (k1 * k1 - k2 * k2) * c * s_,
-                        k1 * k1 * s_ * s_ + k2 * k2 * c * c], dim=-1).reshape(H // 2, W // 2, 2, 2).contiguous()
-    r = torch.rand((H, W), device="cuda", generator=g)
-    cfg = attr_cfg(scale=scale, tile_size=ts)
-    outs = []
-    for bulk in ("0", "1"):
-        os.environ["HHSR_MERGE_BULK"] = bulk
-        try:
-            num = torch.full((scale * H, scale * W, 3), float("nan"), device="cuda")
-            den = torch.full_like(num, 7.0)
-            MG.merge(raw, flow, covs, r, num, den, CFA, cfg, init=True)
-            MG.merge(raw, flow * 0.5, covs, r, num, den, CFA, cfg)
-            torch.cuda.synchronize()
-        finally:
-            os.environ.pop("HHSR_MERGE_BULK", None)
-        outs.append((num, den))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        # the frame-batched fast path (accumulators in registers): 3 frames in one pass == 3 single-frame launches, both
+        # when the batch updates the accumulators and when it initialises them
+        flows = [flow, flow * 0.5 + 0.3, -flow]
+        rs = [r, r * 0.5, 1.0 - r]
+        for init in (False, True):
+            seq_n = torch.rand((scale * H, scale * W, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+            seq_d = seq_n.clone() + 1.0
+            bat_n, bat_d = seq_n.clone(), seq_d.clone()
+            gen_n, gen_d = seq_n.clone(), seq_d.clone()
+            for k in range(3):
+                MG.merge(raw, flows[k], covs, rs[k], seq_n, seq_d, cfa, cfg, init=(init and k == 0))
+            MG.merge_batch([raw] * 3, flows, [covs] * 3, rs, bat_n, bat_d, cfa, cfg, init=init)
+            MG.merge_batch([raw] * 3, flows, [covs] * 3, rs, gen_n, gen_d, cfa, cfg, init=init, generic=True)
+            assert torch.equal(seq_n, bat_n) and torch.equal(seq_d, bat_d), (scale, cfa, kern, init, "batched fast path")
+            assert torch.equal(seq_n, gen_n) and torch.equal(seq_d, gen_d), (scale, cfa, kern, init, "batched generic")
 
 
 @pytest.mark.parametrize("shape", [(64, 96), (70, 100), (37, 53), (5, 8), (3000, 4000)])
