@@ -321,13 +321,19 @@ def load_burst(burst_path):
     return {k: z[k] for k in z.files}
 
 
-def process(burst_path, config):
-    """Host wrapper (super_resolution.py:203-360): load burst, derive the SNR-based parameters exactly like the
-    reference (mutating `config`), run main(), return (np.ndarray [H*s, W*s, 3], debug_dict).  RAW decoding and the
-    CPU ISP post-process are out of scope: the burst comes from an .npz archive and the output is the normalised
-    linear RGB image the reference hands to raw2rgb.postprocess."""
+def process(burst_path, config, output_dtype=None):
+    """Host wrapper (super_resolution.py:203-360): load the burst, derive the SNR-based parameters exactly like the
+    reference (mutating `config`), run main(), then — on the DEVICE, where the reference goes through the host — the
+    frame-count-aware denoisers (:317-331) and raw2rgb.postprocess (:336-349) when the configuration enables them, and
+    return (np.ndarray [H*s, W*s, 3], debug_dict).  RAW decoding is out of scope: the burst comes from an .npz archive
+    (see load_burst; optional keys xyz2cam and orientation stand in for the EXIF tags the reference reads).
+    output_dtype (B200 addition): None / "float32" returns what the reference's process() returns; "uint8" / "uint16"
+    return the quantised image run_handheld.py saves (nan_to_num, clip, rint(x * 255 | 65535)) — a quarter / half of the
+    device-to-host bytes."""
+    from . import raw2rgb
     from .config import Config
     from .noise_model import run_fast_MC
+    from .utils_image import apply_orientation, frame_count_denoising_gauss, frame_count_denoising_median
     data = load_burst(burst_path)
     burst = np.asarray(data["burst"])
     cfa = np.asarray(data.get("cfa_pattern", [[0, 1], [1, 2]])).tolist()
@@ -340,7 +346,13 @@ def process(burst_path, config):
         if "black_levels" not in data or "white_level" not in data:
             raise ValueError("integer burst: the archive must provide black_levels and white_level")
         raw_levels = (np.asarray(data["black_levels"]).reshape(-1).tolist(), int(data["white_level"]))
-        burst = burst.astype(np.uint16)
+        if burst.dtype != np.uint16:
+            # the device path moves uint16 counts; anything else must fit them (the reference casts to float32 without loss)
+            lo, hi = int(burst.min()), int(burst.max())
+            if lo < 0 or hi > 65535 or raw_levels[1] > 65535:
+                raise ValueError("integer burst with samples in [%d, %d] (white level %d) does not fit uint16 sensor counts"
+                                 % (lo, hi, raw_levels[1]))
+            burst = burst.astype(np.uint16)
         ref_raw = RawNormalization(cfa, raw_levels[0], raw_levels[1], wb).apply_numpy(burst[0])
         ref_in, raw_comp = burst[0], burst[1:]
     else:
@@ -366,10 +378,20 @@ def process(burst_path, config):
     config.noise_model.update({"std_curve": std_curve.tolist(), "diff_curve": diff_curve.tolist()})
     ard = config.accumulated_robustness_denoiser
     ard.enabled = bool(any(x.enabled for x in (ard.median, ard.gauss, ard.merge)))
-    if ard.median.enabled or ard.gauss.enabled:
-        raise NotImplementedError("post-merge frame-count denoisers are out of scope (SURVEY section 2, row 17)")
     out, debug_dict = main(ref_in, raw_comp, config)
-    output_image = out.cpu().numpy()
+    if ard.median.enabled:            # super_resolution.py:324-326
+        out = frame_count_denoising_median(out, debug_dict["accumulated robustness"], ard.median, scale=config.scale, mode=config.mode)
+    if ard.gauss.enabled:             # :327-329
+        out = frame_count_denoising_gauss(out, debug_dict["accumulated robustness"], ard.gauss, scale=config.scale, mode=config.mode)
+    post = config.get("postprocessing", None)
+    if post is not None and post.enabled:      # :336-349
+        out = raw2rgb.postprocess(None, out, post.do_color_correction, post.do_tonemapping, post.do_gamma_correction,
+                                  post.sharpening, post.do_devignetting, data.get("xyz2cam", np.zeros((3, 3))),
+                                  output_dtype=output_dtype)
+    elif output_dtype not in (None, "float32"):
+        out = raw2rgb.postprocess(None, out, False, False, False, None, False, None, output_dtype=output_dtype)
+    ori = int(data.get("orientation", 1))      # EXIF 'Image Orientation' (:352-360)
+    output_image = apply_orientation(out.cpu().numpy(), ori)
     if "accumulated robustness" in debug_dict:
-        debug_dict["accumulated robustness"] = debug_dict["accumulated robustness"].cpu().numpy()
+        debug_dict["accumulated robustness"] = apply_orientation(debug_dict["accumulated robustness"].cpu().numpy(), ori)
     return output_image, debug_dict

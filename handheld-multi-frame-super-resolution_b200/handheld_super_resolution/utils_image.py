@@ -78,6 +78,61 @@ def cuda_downsample(th_img, kernel="gaussian", factor=2):
     return out
 
 
+def apply_orientation(img, ori):
+    """EXIF orientation of the output image (utils_image.py:12-56), numpy views on the host."""
+    if ori == 2:
+        img = np.flip(img, axis=1)
+    elif ori == 3:
+        img = np.rot90(img, k=2, axes=(0, 1))
+    elif ori == 4:
+        img = np.flip(img, axis=0)
+    elif ori == 5:
+        img = np.rot90(np.flip(img, axis=1), k=-3, axes=(0, 1))
+    elif ori == 6:
+        img = np.rot90(img, k=-1, axes=(0, 1))
+    elif ori == 7:
+        img = np.rot90(np.flip(img, axis=1), k=-1, axes=(0, 1))
+    elif ori == 8:
+        img = np.rot90(img, k=-3, axes=(0, 1))
+    return img
+
+
+def _frame_count_denoise(entry, image, r_acc, strength, max_frame_count, scale):
+    image = _lib.as_device(image)
+    r_acc = _lib.as_device(r_acc, torch.float64)
+    assert image.ndim == 3 and image.shape[-1] == 3 and r_acc.ndim == 2
+    denoised = torch.empty_like(image)
+    _lib.call(entry, _lib.ptr(image), image.shape[0], image.shape[1], _lib.ptr(r_acc), r_acc.shape[0], r_acc.shape[1],
+              float(scale), float(strength), float(max_frame_count), _lib.ptr(denoised), _lib.stream())
+    return denoised
+
+
+def frame_count_denoising_gauss(image, r_acc, config, scale=None, mode="bayer"):
+    """Gaussian blur of the merged image whose sigma grows where few frames were accumulated (utils_image.py:174-231).
+    `config` is the `accumulated_robustness_denoiser.gauss` node (sigma_max, max_frame_count).  Upstream this stage
+    cannot run: it reads `config.mode` / `config.scale` from that node (:177-178) and iterates range() over a float
+    (:210-215); here mode / scale are arguments (process() passes the main configuration's) and the window half-width is
+    ceil(3 sigma).  Returns a new CUDA tensor."""
+    if config.get("mode", mode) != "bayer":
+        raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
+    scale = config.get("scale", scale)
+    if scale is None:
+        raise ValueError("frame_count_denoising_gauss needs the scale of the merge (config.scale)")
+    return _frame_count_denoise("hhsr_frame_count_denoise_gauss", image, r_acc, config.sigma_max, config.max_frame_count, scale)
+
+
+def frame_count_denoising_median(image, r_acc, config, scale=None, mode="bayer"):
+    """Median filter of the merged image whose radius grows where few frames were accumulated (utils_image.py:233-315):
+    literal bubble sort and upper median like the reference kernel; radius_max <= 7 (the reference's 256-entry window
+    buffer overflows above).  Same remarks on `config` / scale / mode as frame_count_denoising_gauss."""
+    if config.get("mode", mode) != "bayer":
+        raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
+    scale = config.get("scale", scale)
+    if scale is None:
+        raise ValueError("frame_count_denoising_median needs the scale of the merge (config.scale)")
+    return _frame_count_denoise("hhsr_frame_count_denoise_median", image, r_acc, config.radius_max, config.max_frame_count, scale)
+
+
 def computeRMSE(image1, image2):
     """utils_image.py:408-414."""
     assert np.array_equal(image1.shape, image2.shape), "images have different sizes"

@@ -177,6 +177,32 @@ int hhsr_reduce_merge_ref(const float *const *peer_nums, const float *const *pee
                           const int *cfa_host, int iso, const double *acc_rob, int max_frame_count, int rad_max,
                           double max_multiplier, int fuse_divide, int row_begin, int row_end, hhsr_stream_t stream);
 
+/* ---- output side: the host post-process of the reference on the device, so that only
+ * the finished image crosses PCIe.  img: the merged image [H][W][3] float32 (H, W here are the OUTPUT sizes). */
+/* colour matrix + clip (raw2rgb.py:139-146, 224-226): img[p] <- clip(ccm @ img[p], 0, 1) in place; ccm_host: 9 floats,
+ * row-major cam2rgb. */
+int hhsr_post_ccm_clip(float *img, size_t n_px, const float *ccm_host, hhsr_stream_t stream);
+/* unsharp mask (raw2rgb.py:228-238 -> skimage.filters.unsharp_mask -> scipy.ndimage.gaussian_filter(sigma, truncate=4,
+ * mode="reflect")), first pass: Gaussian along the rows axis (axis 0), float64 accumulation, float32 result in tmp.
+ * taps_host: 2*radius+1 float64 weights (radius <= 64). */
+int hhsr_post_blur_cols(const float *img, int H, int W, const double *taps_host, int radius, float *tmp,
+                        hhsr_stream_t stream);
+/* second pass (axis 1) fused with everything that follows (raw2rgb.py:228-250 and run_handheld.py:132-150):
+ * img + (img - blurred) * amount when tmp != NULL (tmp from hhsr_post_blur_cols; NULL: sharpening off), devignetting
+ * (raw2rgb.py:203-210) when devignette != 0, clip to [0,1], x ** inv_gamma when inv_gamma > 0, clip.
+ * out_kind 0: float32 [H][W][3] (NaN kept, what process() returns); 1: uint8, 2: uint16 — nan_to_num, clip,
+ * rint(x * 255 | 65535) (skimage img_as_ubyte / img_as_uint on a float32 image). */
+int hhsr_post_finish(const float *img, const float *tmp, int H, int W, const double *taps_host, int radius, float amount,
+                     int devignette, float inv_gamma, int out_kind, void *out, hhsr_stream_t stream);
+/* frame-count-aware denoisers of the merged image (utils_image.py:174-231 gauss, :233-315 median): acc_rob is the
+ * accumulated robustness float64 [H][W] (raw resolution), img/out [Hs][Ws][3] (out != img).  Upstream these stages
+ * cannot run (see csrc/post.cu); mode/scale come from the main configuration, Gaussian window half-width = ceil(3 sigma),
+ * median radius <= 7. */
+int hhsr_frame_count_denoise_gauss(const float *img, int Hs, int Ws, const double *acc_rob, int H, int W, double scale,
+                                   double sigma_max, double max_frame_count, float *out, hhsr_stream_t stream);
+int hhsr_frame_count_denoise_median(const float *img, int Hs, int Ws, const double *acc_rob, int H, int W, double scale,
+                                    double radius_max, double max_frame_count, float *out, hhsr_stream_t stream);
+
 /* ---- element-wise helpers (utils.py:62-120) */
 int hhsr_divide(float *num, const float *den, size_t n, hhsr_stream_t stream);
 int hhsr_add_f64_f32(double *A, const float *B, size_t n, hhsr_stream_t stream);

@@ -768,3 +768,138 @@ def main(ref_img, comp_imgs, cfg, trace=None):
     dbg["accumulated robustness"] = acc_rob
     dbg["num"], dbg["den"] = num.copy(), den.copy()
     return divide(num, den), dbg
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Output side — raw2rgb.py:139-250, run_handheld.py:132-150, utils_image.py:174-315
+#
+# Parity status of this block.  raw2rgb.postprocess is pinned to the reference's own function (tests/golden/
+# post_cases.npz, generator tests/golden/make_golden_post.py, which runs /root/reference's postprocess() with
+# skimage.filters.unsharp_mask — scikit-image is not installed here — restated on top of the real
+# scipy.ndimage.gaussian_filter it calls).  frame_count_denoising_median is pinned to the reference's kernel run under
+# NUMBA_ENABLE_CUDASIM (same fixture).  frame_count_denoising_gauss is PARITY UNPINNED: upstream it cannot execute
+# (range() over a float, utils_image.py:210-215), neither compiled nor simulated; the one repair (t = ceil(3*sigma)) is ours.
+# --------------------------------------------------------------------------------------------------------------
+def gaussian_taps(sigma, radius):
+    """scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius) (scipy 1.18): float64, normalised, symmetric."""
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return phi / phi.sum()
+
+
+def gaussian_filter_reflect(img, sigma, truncate=4.0):
+    """scipy.ndimage.gaussian_filter(img, sigma, mode='reflect', truncate=4) of a 2-D float32 image: correlate1d along
+    axis 0, then along axis 1; float64 accumulation, each pass rounded to the input dtype (scipy keeps it)."""
+    radius = int(truncate * float(sigma) + 0.5)
+    w = gaussian_taps(sigma, radius)
+    out = np.asarray(img)
+    for axis in (0, 1):
+        pad = [(0, 0), (0, 0)]
+        pad[axis] = (radius, radius)
+        p = np.pad(out.astype(F64), pad, mode="symmetric")      # numpy 'symmetric' == scipy 'reflect' (d c b a | a b c d | d c b a)
+        acc = np.zeros(out.shape, F64)
+        n = out.shape[axis]
+        for k in range(2 * radius + 1):
+            sl = [slice(None), slice(None)]
+            sl[axis] = slice(k, k + n)
+            acc += w[k] * p[tuple(sl)]
+        out = acc.astype(img.dtype)
+    return out
+
+
+def unsharp_mask(img, radius, amount):
+    """skimage.filters.unsharp_mask(img, radius, amount, channel_axis=2, preserve_range=True) (scikit-image 0.2x,
+    filters/_unsharp_mask.py): per channel  image + (image - gaussian(image, sigma=radius, mode='reflect')) * amount,
+    float32 in -> float32 out, no clipping."""
+    img = np.asarray(img, F32)
+    out = np.empty_like(img)
+    for c in range(img.shape[2]):
+        blurred = gaussian_filter_reflect(img[..., c], radius)
+        out[..., c] = img[..., c] + (img[..., c] - blurred) * F32(amount)
+    return out
+
+
+def color_matrix(xyz2cam):
+    """raw2rgb.py:118-136 get_color_matrix -> cam2rgb (:223-224)."""
+    rgb2xyz = np.array([[0.4124564, 0.3575761, 0.1804375], [0.2126729, 0.7151522, 0.0721750], [0.0193339, 0.1191920, 0.9503041]])
+    xyz2cam = np.asarray(xyz2cam)
+    rgb2cam = rgb2xyz if np.linalg.norm(xyz2cam) == 0 else xyz2cam @ rgb2xyz
+    rgb2cam = (rgb2cam / rgb2cam.sum(axis=-1, keepdims=True)).astype(F32)
+    return np.linalg.inv(rgb2cam)
+
+
+def postprocess(img, do_color_correction=True, do_tonemapping=False, do_gamma=True, sharpening=None, do_devignette=False,
+                xyz2cam=None):
+    """raw2rgb.py:212-250 (the `img is not None` branch) on a float32 [H,W,3] image."""
+    img = np.asarray(img, F32)
+    if do_color_correction:
+        cam2rgb = color_matrix(xyz2cam)
+        img = np.clip(np.einsum("ij,hwj->hwi", cam2rgb, img).astype(F32), 0.0, 1.0)         # apply_ccm :139-146
+    if sharpening is not None and sharpening.get("enabled", False):
+        img = unsharp_mask(img, sharpening.get("radius", 3), sharpening.get("amount", 0.5))
+    if do_devignette:                                                                          # :203-210 (float64 from here on)
+        h, w, _ = img.shape
+        vf = np.abs(np.linspace(-h / w * np.pi / 2, h / w * np.pi / 2, h))
+        vf = np.outer(vf, np.abs(np.linspace(-np.pi / 2, np.pi / 2, w)))
+        img = (2 - np.cos(vf) ** 4)[:, :, None] * img
+    if do_tonemapping:
+        raise NotImplementedError("apply_smoothstep (OpenCV MergeMertens, raw2rgb.py:153-170) is outside the restated path")
+    img = np.clip(img, 0.0, 1.0)
+    if do_gamma:
+        img = np.clip(img, 0.0, 1.0) ** (1.0 / 2.2)                                            # gamma_compression :143-146
+    return np.clip(img, 0.0, 1.0)
+
+
+def img_as_ubyte(img, top=255):
+    """run_handheld.py:132-133,150: nan_to_num, clip, skimage.img_as_ubyte of a float32 image = rint(x * 255) in float32."""
+    x = np.clip(np.nan_to_num(np.asarray(img, F32)), 0, 1)
+    return np.rint(x * F32(top)).astype(np.uint8 if top == 255 else np.uint16)
+
+
+def _grey_index(v, scale, n):
+    return min(max(int(round((v - 0.5) / (2 * scale))), 0), n - 1)                            # utils_image.py:204-205 (Python round: half to even)
+
+
+def frame_count_denoising_gauss(image, r_acc, scale, sigma_max, max_frame_count):
+    """utils_image.py:192-231 with t = ceil(3 sigma) (upstream iterates range() over the float 3*sigma and cannot run)."""
+    image = np.asarray(image, F32)
+    Hs, Ws, _ = image.shape
+    out = np.empty_like(image)
+    for y in range(Hs):
+        for x in range(Ws):
+            r = min(r_acc[_grey_index(y, scale, r_acc.shape[0]), _grey_index(x, scale, r_acc.shape[1])], max_frame_count)
+            sigma = sigma_max * (max_frame_count - r) / max_frame_count
+            t = int(math.ceil(3 * sigma))
+            if t <= 0:
+                out[y, x] = image[y, x]
+                continue
+            num, den = np.zeros(3, F64), 0.0
+            for i in range(-t, t + 1):
+                for j in range(-t, t + 1):
+                    if 0 <= y + i < Hs and 0 <= x + j < Ws:
+                        w = math.exp(-(j * j + i * i) / (2 * sigma * sigma))
+                        num += w * image[y + i, x + j].astype(F64)
+                        den += w
+            out[y, x] = (num / den).astype(F32)
+    return out
+
+
+def frame_count_denoising_median(image, r_acc, scale, radius_max, max_frame_count):
+    """utils_image.py:251-315: window radius from the accumulated robustness, literal bubble sort, buffer[k // 2]."""
+    image = np.asarray(image, F32)
+    Hs, Ws, C = image.shape
+    out = np.empty_like(image)
+    for y in range(Hs):
+        for x in range(Ws):
+            r = min(r_acc[_grey_index(y, scale, r_acc.shape[0]), _grey_index(x, scale, r_acc.shape[1])], max_frame_count)
+            radius = min(14, int(round(radius_max * (max_frame_count - r) / max_frame_count)))
+            for c in range(C):
+                buf = [image[y + i, x + j, c] for i in range(-radius, radius + 1) for j in range(-radius, radius + 1)
+                       if 0 <= y + i < Hs and 0 <= x + j < Ws]
+                k = len(buf)
+                for i in range(k - 1):
+                    for j in range(k - i - 1):
+                        if buf[j] > buf[j + 1]:
+                            buf[j], buf[j + 1] = buf[j + 1], buf[j]
+                out[y, x, c] = buf[k // 2]
+    return out

