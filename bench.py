@@ -156,6 +156,13 @@ def oracle_step(burst, cfg, pool):
     return O.divide(num, den)
 
 
+# BASELINE config 1, measured in the build container (CPU only): the reference's own main() under the Numba simulator
+CONFIG1_NOTE = ("the reference has no CPU implementation; its own main() under NUMBA_ENABLE_CUDASIM=1 (BASELINE config 1: 2 frames "
+                "256x256, scale 1, Ts 32, factors [1,2,2,2]) took 1910.5 s on 8 host cores (GIL-bound, ~1 core busy) = 3.4e-5 output "
+                "MPix/s (baseline/run_reference_cudasim.py; output kept as tests/golden/config1_cudasim.npz and checked against "
+                "main() in tests/test_gpu_parity.py) - hence the NumPy oracle port as the timed CPU arm")
+
+
 def cpu_sample(wl, n_frames, crop, cores):
     """Bounded sample of the workload for the CPU arm: an n_frames x crop x crop burst from the same generator, same
     config.  Returns (burst, plain cfg, scaling) with scaling = (sample out MPix) * (n_frames / workload frames): work
@@ -188,13 +195,28 @@ def run_reference_arm(args, wl, wl_name):
     if pool is not None:
         pool.close()
     value = scaling / dt
+    # beside it, when this box has a GPU and the reference copy travelled: the unmodified reference's own Numba-CUDA run
+    # of the WHOLE workload (the reference has no CPU implementation; this is the meaningful "beat this" number)
+    ref_gpu = {"unavailable": "no CUDA device, Numba or baseline/_ref on this box"}
+    script = os.path.join(ROOT, "baseline", "time_reference_numba.py")
+    if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "handheld_super_resolution")):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                p = subprocess.run([sys.executable, script, str(wl["n"]), str(wl["H"]), str(wl["W"]), str(wl["scale"])],
+                                   capture_output=True, text=True, timeout=600)
+                js = [x for x in p.stdout.splitlines() if x.startswith("{")]
+                ref_gpu = json.loads(js[-1]) if js else {"unavailable": (p.stderr or p.stdout)[-300:]}
+        except Exception as e:       # measurement extra: never fails the arm
+            ref_gpu = {"unavailable": repr(e)[:300]}
     sample = ("%d-frame %dx%d crop of the workload per step (same generator and config), comp frames spread over %d "
               "processes; value = sample output MPix x (%d/%d frames) / seconds" % (n_frames, crop, crop, nproc, n_frames, wl["n"]))
     line = {"impl": "reference", "metric": "output MPix/s (20x12MP->48MP burst)", "value": value, "unit": "MPix/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64 mixed (as the reference)",
             "data": "synthetic", "config": workload_config(wl_name, wl, args.gpus),
-            "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": nproc, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": nproc, "kind": "port", "sample": sample, "note": CONFIG1_NOTE},
+            "reference_numba_gpu": ref_gpu,
             "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -202,6 +224,33 @@ def run_reference_arm(args, wl, wl_name):
 # ------------------------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------------------------
+def host_image_buffers(hs, ws, world, rank, n_buffers=2):
+    """Pinned host buffers [hs, ws, 3] float32 for the result.  With several ranks they are views of ONE POSIX
+    shared-memory segment mapped by every rank and page-locked with cudaHostRegister: each rank copies its slice of the
+    image over its own PCIe link and the consumer (rank 0) sees the whole image.  Falls back to private pinned buffers."""
+    import torch
+    nbytes = hs * ws * 3 * 4
+    if world == 1:
+        return [torch.empty((hs, ws, 3), dtype=torch.float32).pin_memory() for _ in range(n_buffers)], "pinned"
+    import torch.distributed as dist
+    path = "/dev/shm/hhsr_bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), hs * ws)
+    try:
+        if rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(nbytes * n_buffers)
+        dist.barrier()
+        flat = torch.from_file(path, shared=True, size=hs * ws * 3 * n_buffers, dtype=torch.float32)
+        rc = torch.cuda.cudart().cudaHostRegister(flat.data_ptr(), nbytes * n_buffers, 0)
+        assert int(rc) == 0, "cudaHostRegister failed (%s)" % rc
+        dist.barrier()
+        if rank == 0:
+            os.unlink(path)          # the mappings keep the segment alive
+        return [flat[i * hs * ws * 3:(i + 1) * hs * ws * 3].view(hs, ws, 3) for i in range(n_buffers)], "shared POSIX shm + cudaHostRegister"
+    except Exception as e:
+        print("shared host image unavailable (%s); private pinned buffers" % e, file=sys.stderr)
+        return [torch.empty((hs, ws, 3), dtype=torch.float32).pin_memory() for _ in range(n_buffers)], "private pinned"
+
+
 def run_cuda_arm(args, wl, wl_name):
     import torch
     import torch.distributed as dist
@@ -217,17 +266,22 @@ def run_cuda_arm(args, wl, wl_name):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, H, W, scale = wl["n"], wl["H"], wl["W"], wl["scale"]
     hs, ws = round(scale * H), round(scale * W)
-    # the one reduction point: fused peer-memory kernel (default when it can be set up) or NCCL reduce-scatter
+    # the one exchange point of a multi-GPU run: "rows" (merge sharded by output rows over NVLink peer memory, default
+    # when symmetric memory can be set up), "p2p" (frame-sharded accumulators summed by one fused peer-memory kernel),
+    # "reduce_scatter" / "allreduce" (the same sum over NCCL)
     reduce_mode = args.reduce
-    if world > 1 and reduce_mode in ("auto", "p2p"):
+    if world > 1 and reduce_mode in ("auto", "rows", "p2p"):
         try:
-            from handheld_super_resolution.distributed import P2PReduce
-            P2PReduce.get((hs, ws, 3))
-            reduce_mode = "p2p"
+            from handheld_super_resolution.distributed import P2PReduce, RowShardedMerge
+            if reduce_mode in ("auto", "rows"):
+                RowShardedMerge.get(H, W, scale, n - 1, 32)
+                reduce_mode = "rows"
+            else:
+                P2PReduce.get((hs, ws, 3))
         except Exception as e:      # no peer access / symmetric memory on this box
-            if args.reduce == "p2p":
+            if args.reduce != "auto":
                 raise
-            print("p2p reduction unavailable (%s); using NCCL reduce-scatter" % e, file=sys.stderr)
+            print("peer-memory exchange unavailable (%s); using NCCL reduce-scatter" % e, file=sys.stderr)
             reduce_mode = "reduce_scatter"
     elif reduce_mode == "auto":
         reduce_mode = "reduce_scatter"
@@ -247,7 +301,7 @@ def run_cuda_arm(args, wl, wl_name):
     burst_u16 = torch.empty((n, H, W), dtype=torch.uint16).pin_memory()
     burst_u16.view(torch.int16).copy_(counts.to(torch.int16))   # bit pattern of the low 16 bits
     del counts, wbn
-    out_hosts = [torch.empty((hs, ws, 3), dtype=torch.float32).pin_memory() for _ in range(2)]   # double-buffered D2H
+    out_hosts, shared_note = host_image_buffers(hs, ws, world, rank)      # double-buffered D2H target, one image for all ranks
     d2h_stream = torch.cuda.Stream()
     d2h_state = {"k": 0, "events": [None, None]}
     torch.cuda.synchronize()
@@ -271,7 +325,7 @@ def run_cuda_arm(args, wl, wl_name):
         e1.record()
         merge_events.append((len(comps), bool(k.get("init")), e0, e1))
     SR.merge, SR.merge_batch = timed_merge, timed_merge_batch
-    batch = args.merge_batch if args.merge_batch > 0 else SR.MERGE_BATCH
+    batch = args.merge_batch if args.merge_batch > 0 else SR.MERGE_BATCH     # 0: automatic (main() decides per call)
     SR.MERGE_BATCH = batch
 
     def step_resident():
@@ -283,10 +337,13 @@ def run_cuda_arm(args, wl, wl_name):
         buffers, so it overlaps the NEXT burst's compute (steady-state throughput of back-to-back bursts); every
         copy still happens inside the timed region, which ends with a full device synchronisation."""
         if u16:
-            out, _ = main_sharded(burst_u16[0], burst_u16[1:], cfg_u16)
+            out, dbg = main_sharded(burst_u16[0], burst_u16[1:], cfg_u16)
         else:
-            out, _ = main_sharded(burst_host[0], burst_host[1:], cfg)
-        if rank == 0:
+            out, dbg = main_sharded(burst_host[0], burst_host[1:], cfg)
+        # who copies what to the host: with the row-sharded merge every rank owns a slice of the image and sends it over
+        # its own PCIe link into the shared host image; otherwise rank 0 holds the whole image
+        rows = dbg.get("rows") if isinstance(dbg, dict) else None
+        if rows is not None or rank == 0:
             k = d2h_state["k"] % 2
             d2h_state["k"] += 1
             if d2h_state["events"][k] is not None:
@@ -296,8 +353,10 @@ def run_cuda_arm(args, wl, wl_name):
             with torch.cuda.stream(d2h_stream if pipelined else torch.cuda.current_stream()):
                 if pipelined:
                     d2h_stream.wait_event(ready)
-                out_hosts[k].copy_(out, non_blocking=True)
-                out.record_stream(torch.cuda.current_stream())
+                dst = out_hosts[k] if rows is None else out_hosts[k][rows[0]:rows[1]]
+                if out is not None and dst.numel() > 0:
+                    dst.copy_(out, non_blocking=True)
+                    out.record_stream(torch.cuda.current_stream())
                 done = torch.cuda.Event()
                 done.record()
             d2h_state["events"][k] = done
@@ -317,6 +376,7 @@ def run_cuda_arm(args, wl, wl_name):
         e0.record()
         for _ in range(steps):
             fn()
+        torch.cuda.current_stream().wait_stream(d2h_stream)      # the last result copy belongs to the timed region
         e1.record()
         barrier()
         t1 = time.perf_counter()
@@ -339,7 +399,7 @@ def run_cuda_arm(args, wl, wl_name):
     # the reference's launch granularity (one comp frame per pass over the accumulators) for comparison: a few steps
     # with the batching switched off; its read-modify-write launches are the kernel round 1 reported
     per_frame_ms = []
-    if batch != 1 and world == 1:
+    if batch != 1 and world == 1 and not args.no_e2e:
         SR.MERGE_BATCH = 1
         step_resident()
         merge_events.clear()
@@ -359,6 +419,53 @@ def run_cuda_arm(args, wl, wl_name):
         ms_u16, _, t2 = timed(lambda: step_e2e(u16=True), args.steps)
     clocks = sampler.stop(t0, t2) if rank == 0 else None
     SR.merge, SR.merge_batch = orig_merge, orig_merge_batch
+    alloc = torch.cuda.memory_stats()
+    alloc_note = {"cudaMalloc_calls_total": int(alloc.get("num_device_alloc", 0)), "alloc_retries": int(alloc.get("num_alloc_retries", 0)),
+                  "reserved_GB": alloc.get("reserved_bytes.all.peak", 0) / 1e9}
+
+    # correctness of the sharded run, outside every timed region: the same burst through the single-GPU path on this
+    # rank, compared with what this rank holds of the sharded result (its row slice, or the whole image on rank 0)
+    parity = None
+    if world > 1:
+        out_s, dbg_s = main_sharded(burst_dev[0], burst_dev[1:], cfg)
+        want, _ = SR.main(burst_dev[0], burst_dev[1:], cfg)
+        rows = dbg_s.get("rows")
+        if rows is not None:
+            want = want[rows[0]:rows[1]]
+        d = torch.zeros(2, device="cuda")
+        if out_s is not None and (rows is not None or rank == 0 or reduce_mode in ("reduce_scatter", "allreduce")) and want.numel() > 0:
+            same_nan = torch.equal(torch.isnan(out_s), torch.isnan(want))
+            d[0] = torch.nan_to_num((out_s - want).abs(), nan=0.0).max()
+            d[1] = 0.0 if same_nan else 1.0
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        parity = {"max_abs_diff": d[0].item(), "nan_pattern_differs": bool(d[1].item() > 0),
+                  "note": "sharded result vs the single-GPU path on the same burst, max over ranks; computed outside the timed regions"}
+        del out_s, want
+
+    # other BASELINE configurations, resident timing only (driver-observed at 8 GPUs: configs 4 and 5)
+    extras = []
+    names = args.extra_workloads
+    names = (["13x12MP_s3", "20x50MP_s2"] if world >= 8 else []) if names == "auto" else [x for x in names.split(",") if x and x != "none"]
+    if names:
+        del burst_dev, burst_host, burst_u16, out_hosts
+        from handheld_super_resolution import distributed as D
+        D.RowShardedMerge._cache.clear(), D.P2PReduce._cache.clear()
+        torch.cuda.empty_cache()
+    for name in names:
+        w2 = WORKLOADS[name]
+        b2, _ = synth_burst(w2["n"], w2["H"], w2["W"], seed=0, device="cuda", as_numpy=False)
+        c2 = make_config(w2["scale"], w2["H"], w2["W"], b2[0].mean().item())
+        fn = lambda: main_sharded(b2[0], b2[1:], c2)      # noqa: E731
+        for _ in range(3):
+            fn()
+        ms2, _, _ = timed(fn, max(3, args.steps // 2))
+        mp = round(w2["scale"] * w2["H"]) * round(w2["scale"] * w2["W"]) / 1e6
+        extras.append({"workload": name, **w2, "ms_per_step": ms2, "value": mp / (ms2 * 1e-3), "unit": "MPix/s", "n_gpus": world,
+                       "note": "resident burst, same call and exchange mode as the main workload"})
+        del b2
+        from handheld_super_resolution import distributed as D
+        D.RowShardedMerge._cache.clear(), D.P2PReduce._cache.clear()
+        torch.cuda.empty_cache()
 
     if rank == 0:
         out_mpix = hs * ws / 1e6
@@ -373,7 +480,7 @@ def run_cuda_arm(args, wl, wl_name):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "merge_traffic_bytes.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("%s_batch%d" % (wl_name, batch))
+            traffic = json.load(open(tp)).get("%s_batch%d" % (wl_name, max(K for K, _, _ in merge_launches) if merge_launches else 0))
         alg1 = merge_algorithmic_bytes(H, W, scale, ny, nx)
         pf_ms = float(np.mean(per_frame_ms)) if per_frame_ms else None
         line = {
@@ -382,10 +489,13 @@ def run_cuda_arm(args, wl, wl_name):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (f64 sub-pixel positions)", "data": "synthetic",
             "config": workload_config(wl_name, wl, world),
-            "reduce": None if world == 1 else (
-                "one fused peer-memory kernel (NVLink pull + sum + merge_ref + divide)" if reduce_mode == "p2p"
-                else "one NCCL reduce-scatter + all-gather of the image"),
-            "merge_batch": batch,
+            "reduce": None if world == 1 else {
+                "rows": "merge sharded by output rows: one exchange of LR row bands over NVLink peer memory, every rank keeps "
+                        "its slice of the image (host copies over the ranks' own PCIe links into one %s image)" % shared_note,
+                "p2p": "frame-sharded accumulators, one fused peer-memory kernel (NVLink pull + sum + merge_ref + divide), image on rank 0",
+                "reduce_scatter": "frame-sharded accumulators, one NCCL reduce-scatter + all-gather of the image",
+                "allreduce": "frame-sharded accumulators, one NCCL all-reduce"}[reduce_mode],
+            "merge_batch": batch if batch > 0 else "auto (whole burst per pass when resident, 5 frames per pass when streamed from the host)",
             "e2e": {"value": out_mpix / (ms_e2e * 1e-3), "unit": "MPix/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(n * H * W * 4), "d2h_bytes_per_step": int(hs * ws * 3 * 4),
                     "mode": "back-to-back bursts, result D2H double-buffered on a copy stream (overlaps the next burst)",
@@ -394,8 +504,9 @@ def run_cuda_arm(args, wl, wl_name):
                                    "h2d_bytes_per_step": int(n * H * W * 2),
                                    "note": "same call fed with 14-bit sensor counts (uint16), normalised on the device"}},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": ("accumulate_pow2_batch_kernel (merge, up to %d comp frames per pass over the accumulators)" % batch)
-                                   if batch > 1 else "accumulate_pow2_kernel (merge, one comp frame per launch)",
+            "roofline": {"kernel": ("accumulate_pow2_batch_kernel (merge, up to %d comp frames per pass over the accumulators)"
+                                    % max(K for K, _, _ in merge_launches)) if frames_total > len(merge_launches)
+                                   else "accumulate_pow2_kernel (merge, one comp frame per launch)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_total / n_launch, "avg_launch_ms": ms_total / n_launch,
@@ -410,7 +521,12 @@ def run_cuda_arm(args, wl, wl_name):
                              "achieved": alg1 / (pf_ms * 1e-3) / 1e9, "frac": alg1 / (pf_ms * 1e-3) / 1e9 / peak,
                              "avg_launch_ms": pf_ms, "algorithmic_bytes_per_launch": alg1, "launches_timed": len(per_frame_ms)}},
             "clocks": clocks,
+            "allocator": alloc_note,
         }
+        if parity is not None:
+            line["parity_vs_single"] = parity
+        if extras:
+            line["extra_workloads"] = extras
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line), flush=True)
@@ -425,7 +541,7 @@ def cpu_baseline(wl):
     t0 = time.perf_counter()
     oracle_step(burst, cfg, None)
     dt = time.perf_counter() - t0
-    return {"value": scaling / dt, "unit": "MPix/s", "cores": 1, "kind": "port", "seconds": dt,
+    return {"value": scaling / dt, "unit": "MPix/s", "cores": 1, "kind": "port", "seconds": dt, "note": CONFIG1_NOTE,
             "sample": "3-frame 704x704 crop of the workload, NumPy oracle in one process; value = sample output MPix x "
                       "(3/%d frames) / seconds (work ~ pixels x frames)" % wl["n"]}
 
@@ -440,8 +556,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--merge-batch", type=int, default=0, help="comp frames per pass over the accumulators (0: the package default)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer legs (e2e fields are NaN)")
-    ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "reduce_scatter", "allreduce"],
-                    help="N > 1: how the frame-sharded accumulators are summed (auto = p2p when available)")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "rows", "p2p", "reduce_scatter", "allreduce"],
+                    help="N > 1: the exchange point (auto = rows, the row-sharded merge, when peer memory is available; "
+                         "p2p / reduce_scatter / allreduce sum frame-sharded accumulators)")
+    ap.add_argument("--extra-workloads", default="auto", help="comma-separated workloads also timed (resident) at N > 1; "
+                    "auto = 13x12MP_s3,20x50MP_s2 at 8 GPUs, none otherwise")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

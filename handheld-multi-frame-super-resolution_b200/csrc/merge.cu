@@ -52,6 +52,7 @@ struct MergeGeom {
     double scale, inv_scale;
     bool pow2;      // scale is a power of two: x / scale == x * (1/scale) exactly
     int ts_shift;   // log2(ts) when ts is a power of two, else -1
+    int row_begin, row_end;   // output rows processed by the batched kernels (0, Hs unless row-sharded)
 };
 
 __device__ __forceinline__ int tile_of(int i, const MergeGeom &g) { return g.ts_shift >= 0 ? (i >> g.ts_shift) : (i / g.ts); }
@@ -76,7 +77,7 @@ static MergeGeom make_geom(int H, int W, int nx, int ts, int Hs, int Ws, const i
     int shift = -1;
     for (int k = 0; k < 16; ++k)
         if ((1 << k) == ts) shift = k;
-    return MergeGeom{H, W, nx, ts, H / 2, W / 2, Hs, Ws, make_cfa(cfa), scale, 1.0 / scale, pow2, shift};
+    return MergeGeom{H, W, nx, ts, H / 2, W / 2, Hs, Ws, make_cfa(cfa), scale, 1.0 / scale, pow2, shift, 0, Hs};
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -605,9 +606,9 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_BATCH_MINBLOCKS) accumulate_po
                                                                                             float *__restrict__ den) {
     constexpr int SH = K + 1, MASK = (1 << SH) - 1;
     constexpr float INV = 1.0f / (float)(1 << SH);
-    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int hr_i = g.row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (hr_i >= g.Hs || j0 >= g.Ws) return;
+    if (hr_i >= g.row_end || j0 >= g.Ws) return;
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
     AddSink sink;
     if (STORE) {
@@ -651,9 +652,9 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_BATCH_MINBLOCKS) accumulate_po
 template <bool ISO, int VEC, bool STORE>
 __global__ void __launch_bounds__(256, 2) accumulate_batch_kernel(const __grid_constant__ MergeBatch b, const __grid_constant__ MergeGeom g,
                                                                   float *__restrict__ num, float *__restrict__ den) {
-    const int hr_i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int hr_i = g.row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (hr_i >= g.Hs || j0 >= g.Ws) return;
+    if (hr_i >= g.row_end || j0 >= g.Ws) return;
     const size_t base = ((size_t)hr_i * g.Ws + j0) * 3;
     const bool full = (VEC == 4) && (j0 + VEC <= g.Ws);
     float n[VEC * 3], d[VEC * 3];
@@ -955,7 +956,7 @@ static int check_merge_args(const void *raw, const void *num, const void *den, i
 template <int VEC, bool STORE>
 static void launch_accumulate_vec(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso, dim3 grid,
                                   dim3 block, cudaStream_t st) {
-    if (b.K == 1) {
+    if (b.K == 1 && g.row_begin == 0 && g.row_end == g.Hs) {
         if (iso)
             accumulate_kernel<true, VEC, STORE><<<grid, block, 0, st>>>(b.f[0], g, num, den);
         else
@@ -979,7 +980,7 @@ static int pow2_fast_shift(const MergeGeom &g) {
 template <int K, bool STORE>
 static void launch_pow2(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso, dim3 grid, dim3 block,
                         cudaStream_t st) {
-    if (b.K == 1) {
+    if (b.K == 1 && g.row_begin == 0 && g.row_end == g.Hs) {
         if (iso)
             accumulate_pow2_kernel<true, K, STORE><<<grid, block, 0, st>>>(b.f[0], g, num, den);
         else
@@ -997,17 +998,18 @@ static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num
                              cudaStream_t st) {
     dim3 block(32, 8);
     const int k = generic ? -1 : pow2_fast_shift(g);
+    const int rows = g.row_end - g.row_begin;
     if (k >= 0) {
-        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8));
+        dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(rows, 8));
         if (k == 0) launch_pow2<0, STORE>(b, g, num, den, iso, grid, block, st);
         if (k == 1) launch_pow2<1, STORE>(b, g, num, den, iso, grid, block, st);
         if (k == 2) launch_pow2<2, STORE>(b, g, num, den, iso, grid, block, st);
         return launch_status("merge_accumulate");
     }
     if (g.Ws % 4 == 0)
-        launch_accumulate_vec<4, STORE>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32 * 4), ceil_div(g.Hs, 8)), block, st);
+        launch_accumulate_vec<4, STORE>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32 * 4), ceil_div(rows, 8)), block, st);
     else
-        launch_accumulate_vec<1, STORE>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32), ceil_div(g.Hs, 8)), block, st);
+        launch_accumulate_vec<1, STORE>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32), ceil_div(rows, 8)), block, st);
     return launch_status("merge_accumulate");
 }
 
@@ -1017,14 +1019,18 @@ using namespace hhsr;
 
 static int merge_frames(const float *const *raws, const float *const *flows, const float *const *covs, const float *const *rs,
                         int K, int H, int W, int ny, int nx, int ts, float *num, float *den, int Hs, int Ws, double scale,
-                        const int *cfa_host, int iso, int flags, hhsr_stream_t stream) {
+                        const int *cfa_host, int iso, int flags, int row_begin, int row_end, hhsr_stream_t stream) {
     HHSR_REQUIRE((flags & ~(HHSR_MERGE_INIT | HHSR_MERGE_GENERIC)) == 0, "unknown merge flag");
+    HHSR_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= Hs, "row range must satisfy 0 <= begin < end <= Hs");
     const bool generic = (flags & HHSR_MERGE_GENERIC) != 0;
     HHSR_REQUIRE(raws && flows && rs && K > 0, "null frame list");
     HHSR_REQUIRE(iso || covs, "covs required for the steerable kernel");
     if (int e = check_merge_args(raws[0], num, den, H, W, Hs, Ws, scale, cfa_host)) return e;
     HHSR_REQUIRE(ts > 0 && ny * ts >= H && nx * ts >= W, "flow grid does not cover the frame");
     MergeGeom g = make_geom(H, W, nx, ts, Hs, Ws, cfa_host, scale);
+    g.row_begin = row_begin, g.row_end = row_end;
+    // num / den point at row `row_begin` (a caller may own only that slice); the kernels index rows absolutely
+    num -= (size_t)row_begin * Ws * 3, den -= (size_t)row_begin * Ws * 3;
     for (int k0 = 0; k0 < K; k0 += kMaxBatch) {
         MergeBatch b;
         b.K = (K - k0 < kMaxBatch) ? K - k0 : kMaxBatch;
@@ -1046,19 +1052,27 @@ extern "C" int hhsr_merge_accumulate_batch(const float *const *raws, const float
                                            const float *const *covs, const float *const *rs, int K, int H, int W,
                                            int ny, int nx, int ts, float *num, float *den, int Hs, int Ws,
                                            double scale, const int *cfa_host, int iso, int flags, hhsr_stream_t stream) {
-    return merge_frames(raws, flows, covs, rs, K, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, flags, stream);
+    return merge_frames(raws, flows, covs, rs, K, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, flags, 0, Hs, stream);
+}
+
+extern "C" int hhsr_merge_accumulate_rows(const float *const *raws, const float *const *flows, const float *const *covs,
+                                          const float *const *rs, int K, int H, int W, int ny, int nx, int ts,
+                                          float *num_rows, float *den_rows, int Hs, int Ws, double scale, const int *cfa_host,
+                                          int iso, int flags, int row_begin, int row_end, hhsr_stream_t stream) {
+    return merge_frames(raws, flows, covs, rs, K, H, W, ny, nx, ts, num_rows, den_rows, Hs, Ws, scale, cfa_host, iso, flags,
+                        row_begin, row_end, stream);
 }
 
 extern "C" int hhsr_merge_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
                                      const float *covs, const float *r, float *num, float *den, int Hs, int Ws,
                                      double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
-    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, 0, stream);
+    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, 0, 0, Hs, stream);
 }
 
 extern "C" int hhsr_merge_init_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,
                                           const float *covs, const float *r, float *num, float *den, int Hs, int Ws,
                                           double scale, const int *cfa_host, int iso, hhsr_stream_t stream) {
-    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, HHSR_MERGE_INIT, stream);
+    return merge_frames(&raw, &flow, &covs, &r, 1, H, W, ny, nx, ts, num, den, Hs, Ws, scale, cfa_host, iso, HHSR_MERGE_INIT, 0, Hs, stream);
 }
 
 static int launch_merge_ref(const float *raw, const float *covs, const MergeGeom &g, float *num, float *den, int iso,
@@ -1099,6 +1113,18 @@ extern "C" int hhsr_merge_ref(const float *raw, int H, int W, const float *covs,
     peers.n = 0;
     return launch_merge_ref(raw, covs, g, num, den, iso, acc_rob, max_frame_count, rad_max, max_multiplier, fuse_divide,
                             row_begin, row_end, peers, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int hhsr_merge_ref_rows(const float *raw, int H, int W, const float *covs, float *num_rows, float *den_rows, int Hs, int Ws,
+                                   double scale, const int *cfa_host, int iso, const double *acc_rob, int max_frame_count,
+                                   int rad_max, double max_multiplier, int fuse_divide, int row_begin, int row_end,
+                                   hhsr_stream_t stream) {
+    HHSR_REQUIRE(num_rows && den_rows, "null pointer");
+    HHSR_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= Hs && Ws > 0, "row range must satisfy 0 <= begin < end <= Hs");
+    // the slices start at row `row_begin`; the kernel indexes rows absolutely
+    const size_t off = (size_t)row_begin * Ws * 3;
+    return hhsr_merge_ref(raw, H, W, covs, num_rows - off, den_rows - off, Hs, Ws, scale, cfa_host, iso, acc_rob, max_frame_count,
+                          rad_max, max_multiplier, fuse_divide, row_begin, row_end, stream);
 }
 
 extern "C" int hhsr_reduce_merge_ref(const float *const *peer_nums, const float *const *peer_dens, int n_peers,

@@ -43,6 +43,11 @@ SIGNATURES = {
     "hhsr_merge_accumulate_batch": [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _I,
                                     _I, _P, _P, _I, _I, _D, _IP, _I, _I, _P],
     "hhsr_merge_ref": [_P, _I, _I, _P, _P, _P, _I, _I, _D, _IP, _I, _P, _I, _I, _D, _I, _I, _I, _P],
+    "hhsr_merge_accumulate_rows": [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _I,
+                                   _I, _P, _P, _I, _I, _D, _IP, _I, _I, _I, _I, _P],
+    "hhsr_merge_ref_rows": [_P, _I, _I, _P, _P, _P, _I, _I, _D, _IP, _I, _P, _I, _I, _D, _I, _I, _I, _P],
+    "hhsr_gather_bands": [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
+                          C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "hhsr_normalize_raw_u16": [_P, _I, _I, _FP, _FP, _FP, _P, _P],
     "hhsr_reduce_merge_ref": [C.POINTER(_P), C.POINTER(_P), _I, _P, _I, _I, _P, _P, _I, _I, _D, _IP, _I, _P, _I, _I, _D, _I,
                               _I, _I, _P],
@@ -51,6 +56,7 @@ SIGNATURES = {
     "hhsr_post_finish": [_P, _P, _I, _I, _DP, _I, _F, _I, _F, _I, _P, _P],
     "hhsr_frame_count_denoise_gauss": [_P, _I, _I, _P, _I, _I, _D, _D, _D, _P, _P],
     "hhsr_frame_count_denoise_median": [_P, _I, _I, _P, _I, _I, _D, _D, _D, _P, _P],
+    "hhsr_noise_mc": [_P, _I, _D, _D, _I, C.c_ulonglong, _P, _P, _P],
     "hhsr_divide": [_P, _P, _Z, _P],
     "hhsr_add_f64_f32": [_P, _P, _Z, _P],
     "hhsr_add_many_f64_f32": [_P, C.POINTER(_P), _I, _Z, _P],

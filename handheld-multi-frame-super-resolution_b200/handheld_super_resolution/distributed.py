@@ -121,18 +121,159 @@ class P2PReduce:
         nums = (C.c_void_p * self.world)(*self.peer_ptrs)
         dens = (C.c_void_p * self.world)(*[p + 4 * self.numel for p in self.peer_ptrs])
         r0, r1 = self.rows()
-        _lib.call("hhsr_reduce_merge_ref", nums, dens, self.world, _lib.ptr(ref_img), H, W, _lib.ptr(None if iso else covs),
-                  C.c_void_p(self.peer_ptrs[0]), self.shape[0], self.shape[1], float(config.scale),
-                  _lib.cfa_array(cfa_pattern), int(iso), _lib.ptr(acc), max_fc, rad_max, max_mult, 1, r0, r1, _lib.stream())
-        self.hdl.barrier(channel=1)                 # all slices delivered; peers may reuse their accumulators
-        return num                                  # the whole image on rank 0 only
+        try:
+            if r1 > r0:       # an empty slice (tiny images) has nothing to launch but must still reach the second barrier
+                _lib.call("hhsr_reduce_merge_ref", nums, dens, self.world, _lib.ptr(ref_img), H, W, _lib.ptr(None if iso else covs),
+                          C.c_void_p(self.peer_ptrs[0]), self.shape[0], self.shape[1], float(config.scale),
+                          _lib.cfa_array(cfa_pattern), int(iso), _lib.ptr(acc), max_fc, rad_max, max_mult, 1, r0, r1, _lib.stream())
+        finally:
+            self.hdl.barrier(channel=1)                 # all slices delivered; peers may reuse their accumulators
+        # the symmetric accumulators are overwritten by the next burst: hand out a private copy (rank 0 holds the whole image)
+        return num.clone() if self.rank == 0 else num
+
+
+def equal_row_slices(Hs, world, multiple=8):
+    """Output-row slices [(begin, end)] of the row-sharded merge: as equal as possible, cut at multiples of `multiple`
+    rows (the merge kernels work on blocks of 8 rows), never empty while Hs >= world * multiple."""
+    blocks = -(-Hs // multiple)
+    cuts = [min(Hs, multiple * ((blocks * r) // world)) for r in range(world)] + [Hs]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class RowShardedMerge:
+    """Mode "rows": frames are sharded over ranks for alignment, robustness and kernel estimation; the MERGE is sharded by
+    OUTPUT ROWS.  Each rank publishes the products of its frames (raw frame, flow, covariances, robustness: 144 MB per
+    12 MP frame) in symmetric memory (torch.distributed._symmetric_memory: one allocation mapped into every rank over
+    NVLink / NVSwitch).  After ONE device-side barrier — the only exchange point of the pipeline — a rank pulls, for
+    every frame of the burst, just the LR row band its slice of output rows can touch (hhsr_gather_bands, extents derived
+    on the device from the flow) and merges ALL frames in one pass with the accumulators in registers
+    (hhsr_merge_accumulate_rows), then adds the reference frame and divides (hhsr_merge_ref_rows).
+
+    Against the frame-sharded sum of accumulators ("p2p" / "reduce_scatter"): per rank ~0.3 GB instead of 1.0 GB cross
+    NVLink at 8 GPUs for a 20 x 12 MP burst, nothing is summed across ranks, the merge work is balanced whatever the
+    number of frames per rank, and — frames being accumulated in burst order by the same kernel — the image is
+    BIT-IDENTICAL to the single-GPU result.  Each rank ends with its own slice of the image ([rows, Ws, 3]); nothing is
+    gathered (the host-to-host path copies the slices over the ranks' own PCIe links)."""
+    _cache = {}
+
+    def __init__(self, H, W, scale, n_comp, ts, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.H, self.W, self.scale, self.n_comp, self.ts = H, W, scale, n_comp, ts
+        self.Hs, self.Ws = round(scale * H), round(scale * W)
+        if self.Ws % 4 != 0 or W % 4 != 0 or H % 2 != 0:
+            raise ValueError("row-sharded merge needs W and the output width to be multiples of 4")
+        self.ny, self.nx = -(-H // ts), -(-W // ts)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.slots = max(1, -(-n_comp // self.world))
+        # per slot: raw [H,W] | r [H,W] | covs [H/2,W/2,4] | flow [ny,nx,2] (padded to 4 floats)
+        self.n_plane, self.n_flow = H * W, -(-(self.ny * self.nx * 2) // 4) * 4
+        self.slot_floats = 3 * self.n_plane + self.n_flow
+        self.sym = symm_mem.empty((self.slots * self.slot_floats,), dtype=torch.float32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.sym, self.group)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        # local full-size planes of every frame of the burst (only the gathered bands are ever written / read)
+        self.local = torch.empty((n_comp * self.slot_floats,), dtype=torch.float32, device=dev)
+        self.extents = torch.zeros((max(n_comp, 1), 4), dtype=torch.int32, device=dev)
+        self.row_slice = equal_row_slices(self.Hs, self.world)[self.rank]
+        rows = self.row_slice[1] - self.row_slice[0]
+        self.num = torch.empty((rows, self.Ws, 3), dtype=torch.float32, device=dev)
+        self.den = torch.empty((rows, self.Ws, 3), dtype=torch.float32, device=dev)
+        self.n_local = 0
+
+    @classmethod
+    def get(cls, H, W, scale, n_comp, ts, group=None):
+        key = (H, W, scale, n_comp, ts, id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(H, W, scale, n_comp, ts, group)
+        return cls._cache[key]
+
+    def _slot_views(self, flat, j):
+        b = flat[j * self.slot_floats:(j + 1) * self.slot_floats]
+        n, H, W = self.n_plane, self.H, self.W
+        return (b[:n].view(H, W), b[n:2 * n].view(H, W), b[2 * n:3 * n].view(H // 2, W // 2, 2, 2),
+                b[3 * n:3 * n + self.ny * self.nx * 2].view(self.ny, self.nx, 2))
+
+    def outputs(self, k):
+        """Where main() writes the robustness and covariances of this rank's k-th frame: straight into its slot."""
+        _, r_s, covs_s, _ = self._slot_views(self.sym, k)
+        return r_s, covs_s
+
+    def publish(self, k, im_id, frame, flow, covs, r):
+        """Publish the products of this rank's k-th frame (burst index im_id, owner im_id % world, slot im_id // world)."""
+        assert im_id % self.world == self.rank and im_id // self.world == k < self.slots
+        raw_s, r_s, covs_s, flow_s = self._slot_views(self.sym, k)
+        raw_s.copy_(frame), flow_s.copy_(flow)
+        if r.data_ptr() != r_s.data_ptr():
+            r_s.copy_(r)
+        if covs is not None and covs.data_ptr() != covs_s.data_ptr():
+            covs_s.copy_(covs)
+        self.n_local = k + 1
+
+    def finalize(self, ref_img, covs_ref, num, den, acc_rob, cfa_pattern, config):
+        import ctypes as C
+        from . import _lib
+        from .utils import add_many
+        n, world = self.n_comp, self.world
+        iso = config.merging.kernel == "iso"
+        r0, r1 = self.row_slice
+        rows = r1 - r0
+        out = torch.empty((rows, self.Ws, 3), dtype=torch.float32, device=self.num.device) if rows > 0 else None
+        self.hdl.barrier(channel=0)                 # every rank has published its frames: THE exchange point
+        try:
+            if rows > 0 and n > 0:
+                F = self.slot_floats * 4
+                src = [self.peer_ptrs[f % world] + (f // world) * F for f in range(n)]
+                own = [f % world == self.rank for f in range(n)]
+                dst = [src[f] if own[f] else self.local.data_ptr() + f * F for f in range(n)]
+                P = 4 * self.n_plane
+                arr = lambda xs: (C.c_void_p * n)(*xs)  # noqa: E731
+                lr0 = int(r0 / self.scale)
+                lr1 = min(self.H, int(-(-r1 // self.scale)) + 1)
+                _lib.call("hhsr_gather_bands", arr(src), arr([p + P for p in src]), arr([0 if iso else p + 2 * P for p in src]),
+                          arr([p + 3 * P for p in src]), arr(dst), arr([p + P for p in dst]),
+                          arr([0 if iso else p + 2 * P for p in dst]), arr([p + 3 * P for p in dst]), n, self.H, self.W,
+                          self.ny, self.nx, int(self.ts), lr0, lr1, _lib.ptr(self.extents), _lib.stream())
+                _lib.call("hhsr_merge_accumulate_rows", arr(dst), arr([p + 3 * P for p in dst]),
+                          arr([0 if iso else p + 2 * P for p in dst]), arr([p + P for p in dst]), n, self.H, self.W, self.ny,
+                          self.nx, int(self.ts), _lib.ptr(self.num), _lib.ptr(self.den), self.Hs, self.Ws, float(self.scale),
+                          _lib.cfa_array(cfa_pattern), int(iso), 1, r0, r1, _lib.stream())
+                if acc_rob is not None:
+                    # accumulated robustness of the LR rows [lr0, lr1) this slice looks at (merge_ref reads it at
+                    # rint(oy / scale)): the sum over ALL frames in burst order, from the gathered bands; the other rows
+                    # keep this rank's frames only
+                    def r_rows(f):
+                        flat, j = (self.sym, f // world) if own[f] else (self.local, f)
+                        start = j * self.slot_floats + self.n_plane + lr0 * self.W
+                        return flat[start:start + (lr1 - lr0) * self.W].view(lr1 - lr0, self.W)
+                    acc_rob[lr0:lr1].zero_()
+                    add_many(acc_rob[lr0:lr1], [r_rows(f) for f in range(n)])
+            elif rows > 0:
+                self.num.zero_(), self.den.zero_()
+            if rows > 0:
+                ard = config.accumulated_robustness_denoiser
+                if ard.enabled:
+                    acc, rad_max, max_mult, max_fc = acc_rob, int(ard.merge.rad_max), float(ard.merge.max_multiplier), int(ard.merge.max_frame_count)
+                else:
+                    acc, rad_max, max_mult, max_fc = None, 0, 0.0, 0
+                _lib.call("hhsr_merge_ref_rows", _lib.ptr(ref_img), self.H, self.W, _lib.ptr(None if iso else covs_ref),
+                          _lib.ptr(self.num), _lib.ptr(self.den), self.Hs, self.Ws, float(self.scale), _lib.cfa_array(cfa_pattern),
+                          int(iso), _lib.ptr(acc), max_fc, rad_max, max_mult, 1, r0, r1, _lib.stream())
+                out.copy_(self.num)
+        finally:
+            self.hdl.barrier(channel=1)             # all bands pulled: the owners may overwrite their slots (next burst)
+        return out
 
 
 def main_sharded(ref_img, comp_imgs, config, group=None, mode=None):
-    """main() with the comp frames of this rank only and one sum of the accumulators at the reduction point
-    (mode "reduce_scatter", default, "allreduce", or "p2p" — the fused peer-memory kernel, see P2PReduce; env
-    HHSR_SHARD_REDUCE overrides).  With the NCCL modes every rank returns the full normalised image (identical up to
-    float32 summation order); with "p2p" only rank 0 does."""
+    """main() with the comp frames of this rank only and ONE exchange point after the frame loop:
+      "reduce_scatter" (default) / "allreduce": the frame-sharded accumulators are summed over NCCL; every rank returns
+          the full normalised image (identical up to float32 summation order);
+      "p2p": the same sum as one fused peer-memory kernel (P2PReduce); only rank 0 returns the whole image;
+      "rows": the merge itself is sharded by output rows (RowShardedMerge): every rank returns ITS slice
+          [rows, Ws, 3] of the image, debug_dict["rows"] = (begin, end); bit-identical to the single-GPU image.
+    env HHSR_SHARD_REDUCE overrides the default."""
     import os
     from .super_resolution import main
     if dist.is_available() and dist.is_initialized():
@@ -141,6 +282,12 @@ def main_sharded(ref_img, comp_imgs, config, group=None, mode=None):
         rank, world = 0, 1
     mode = mode or os.environ.get("HHSR_SHARD_REDUCE", "reduce_scatter")
     ids = shard_frames(len(comp_imgs), rank, world)
+    if mode == "rows" and world > 1:
+        H, W = ref_img.shape
+        rs = RowShardedMerge.get(H, W, config.scale, len(comp_imgs), int(config.block_matching.tuning.tile_size), group)
+        out, dbg = main(ref_img, comp_imgs, config, frame_ids=ids, frame_sink=rs, finalize_fn=rs.finalize)
+        dbg["rows"] = rs.row_slice
+        return out, dbg
     if mode == "p2p" and world > 1:
         H, W = ref_img.shape
         s = config.scale

@@ -116,16 +116,18 @@ def ref_noise_terms(ref_local_means, ref_local_stds, table):
     return terms
 
 
-def local_min(R, acc_rob=None):
-    """5x5 local minimum (Alg. 9, robustness.py:641-687); optionally fused with `acc_rob += r` (utils.add)."""
+def local_min(R, acc_rob=None, out=None):
+    """5x5 local minimum (Alg. 9, robustness.py:641-687); optionally fused with `acc_rob += r` (utils.add).
+    `out`: caller-owned result buffer (e.g. a symmetric-memory slot of the row-sharded multi-GPU merge)."""
     R = _lib.as_device(R)
-    r = torch.empty_like(R)
+    r = torch.empty_like(R) if out is None else out
+    assert r.shape == R.shape and r.dtype == torch.float32 and r.is_contiguous() and r.data_ptr() != R.data_ptr()
     _lib.call("hhsr_local_min5", _lib.ptr(R), R.shape[0], R.shape[1], _lib.ptr(r), _lib.ptr(acc_rob), _lib.stream())
     return r
 
 
 def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pattern, white_balance, noise_model,
-                       config, acc_rob=None, return_R=False, generic=False):
+                       config, acc_rob=None, return_R=False, generic=False, out=None):
     """Robustness map r [H, W] of comp frame J_n (Alg. 6, robustness.py:79-170).  Three launches: guide statistics
     at half resolution, the fused per-pixel kernel (warp, distance, noise model, S, threshold), 5x5 minimum (plus,
     for the first comp frame of a burst, the reference-side noise terms).
@@ -134,6 +136,8 @@ def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pat
     comp_img = _lib.as_device(comp_img)
     H, W = comp_img.shape
     if not config.robustness.enabled:
+        if out is not None:
+            return out.fill_(1.0)
         return torch.ones((H, W), dtype=torch.float32, device=comp_img.device)
     if config.mode != "bayer":
         raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
@@ -148,5 +152,5 @@ def compute_robustness(comp_img, ref_local_means, ref_local_stds, flows, cfa_pat
     _lib.call("hhsr_robustness", _lib.ptr(comp_means), _lib.ptr(ref_local_means), _lib.ptr(terms), H, W,
               _lib.ptr(flows), flows.shape[0], flows.shape[1], int(ts),
               float(tun.t), float(tun.s1), float(tun.s2), float(tun.Mt), _lib.ptr(R), int(bool(generic)), _lib.stream())
-    r = local_min(R, acc_rob)
+    r = local_min(R, acc_rob, out=out)
     return (r, R) if return_R else r

@@ -51,7 +51,10 @@ def _align_stream(device, i=0):
 ALIGN_AHEAD = int(os.environ.get("HHSR_ALIGN_AHEAD", "1"))   # alignment chains in flight ahead of the merge (0: one stream)
 # comp frames merged per pass over the accumulators (merge_batch): their raw / flow / covariance / robustness arrays
 # stay resident (144 MB per 12 MP frame) until the batch is merged.  1 = the reference's one launch per frame.
-MERGE_BATCH = int(os.environ.get("HHSR_MERGE_BATCH", "24"))
+# 0 = automatic: the whole burst in one pass (up to 24 frames) when the frames are already on the device — least
+# accumulator traffic — and 5 frames per pass when they stream in from the host, so that merging overlaps the uploads
+# and only the last short batch is left when the last frame arrives.
+MERGE_BATCH = int(os.environ.get("HHSR_MERGE_BATCH", "0"))
 
 
 def _host_tensor(frame):
@@ -77,7 +80,8 @@ class FrameFeeder:
     compute stream; uint16 frames (sensor counts) cross PCIe as 2 bytes per pixel and are normalised on the device
     (utils_dng.RawNormalization, the reference's utils_dng.py:146-160).  CUDA float32 frames pass through."""
     # frame being merged + frames being aligned + frame being uploaded (+ batch - 1 frames waiting in a merge batch)
-    SLOTS = int(os.environ.get("HHSR_STAGING_SLOTS", str(2 + max(ALIGN_AHEAD, 1))))
+    # The uploads of the next frames (and of the next burst) run ahead of the compute stream as far as free slots allow.
+    SLOTS = int(os.environ.get("HHSR_STAGING_SLOTS", "12"))
     _RINGS = {}     # (device, compute stream, role, shape, dtype, slot) -> [buffer, event "slot free"]: staging buffers live
                     # across bursts, so the first uploads of burst i+1 need not wait for the compute stream to drain burst i
 
@@ -149,7 +153,8 @@ class FrameFeeder:
             item[2][1] = ev
 
 
-def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulators=None, finalize_fn=None, merge_batch_size=None):
+def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulators=None, finalize_fn=None, merge_batch_size=None,
+         frame_sink=None):
     """Device pipeline (super_resolution.py:41-200).
 
     ref_img [H,W], comp_imgs [N-1,H,W]: float32 host arrays (numpy / pinned torch) or CUDA tensors.
@@ -161,7 +166,10 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     (e.g. peer-mapped symmetric memory; zeroed here) and `finalize_fn(ref_img, covs, num, den, acc_rob, cfa, config)`
     replaces reduction + merge_ref + divide by one fused step (distributed.P2PReduce) and returns the image.
     `merge_batch_size` (default MERGE_BATCH): comp frames accumulated per pass over num/den (merge.merge_batch; the result
-    is bit-identical for every batch size)."""
+    is bit-identical for every batch size).  `frame_sink` (with finalize_fn): an object with `outputs(k) -> (r, covs)`
+    (buffers the k-th frame's robustness and covariances are written into) and `publish(k, im_id, frame, flow, covs, r)`:
+    the aligned frames are handed over instead of being merged here and no accumulators are allocated — the row-sharded
+    multi-GPU merge (distributed.RowShardedMerge) merges all frames of all ranks into this rank's slice of output rows."""
     verbose_2 = config.verbose >= 2
     grey_method = config.grey_method
     if config.mode != "bayer":
@@ -205,7 +213,10 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     ids = list(range(n_images) if frame_ids is None else frame_ids)
     # the first comp frame initialises the accumulators (merge(init=True)); only a burst/shard without comp frames
     # needs them zero-filled (the reference uploads host zeros, super_resolution.py:123-124)
-    if accumulators is not None:
+    if frame_sink is not None:
+        assert finalize_fn is not None, "frame_sink needs a finalize_fn that produces the image"
+        num = den = None
+    elif accumulators is not None:
         num, den = accumulators
         assert tuple(num.shape) == (*output_size, 3) and tuple(den.shape) == (*output_size, 3)
         if not ids:
@@ -217,7 +228,10 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     accumulated_r = torch.zeros((H, W), dtype=torch.float64, device=dev) if accumulate_r else None
 
     _mark("ref_side")
-    batch_size = max(1, int(MERGE_BATCH if merge_batch_size is None else merge_batch_size))
+    batch_size = int(MERGE_BATCH if merge_batch_size is None else merge_batch_size)
+    if batch_size <= 0:
+        on_device = all(isinstance(comp_imgs[i], torch.Tensor) and comp_imgs[i].is_cuda for i in ids)
+        batch_size = 24 if on_device else 5
     feed = FrameFeeder(comp_imgs, ids, config, dev, extra_slots=batch_size - 1)
     pending = []        # (k, frame, flow, covs, r) of the frames waiting for the next pass over the accumulators
     merged_any = False
@@ -254,9 +268,16 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
             flow.record_stream(main_stream)
         if debug_mode:
             debug_dict["flow"].append(flow.cpu().numpy())
+        r_out, covs_out = frame_sink.outputs(k) if frame_sink is not None else (None, None)
         r = compute_robustness_(cuda_img, ref_local_means, ref_local_stds, flow, cfa_pattern, white_balance,
-                                noise_tab, config)
-        covs = estimate_kernels_(cuda_img, config)
+                                noise_tab, config, out=r_out)
+        covs = estimate_kernels_(cuda_img, config, out=covs_out)
+        if frame_sink is not None:
+            frame_sink.publish(k, im_id, cuda_img, flow, covs, r)
+            if accumulate_r:
+                add_many(accumulated_r, [r])
+            feed.release(k)
+            continue
         pending.append((k, cuda_img, flow, covs, r))
         if len(pending) == batch_size or k == len(ids) - 1:
             # one pass over num/den for the whole batch; the first batch of a burst initialises them

@@ -167,6 +167,30 @@ int hhsr_merge_ref(const float *raw, int H, int W, const float *covs, float *num
                    int rad_max, double max_multiplier, int fuse_divide, int row_begin, int row_end,
                    hhsr_stream_t stream);
 
+/* ---- row-sharded merge across GPUs (a B200 addition, the reference is single-GPU).  Frames are
+ * sharded over ranks up to the merge; each rank then merges ALL frames into its own slice of output rows and needs, from
+ * every frame's owner, only the LR row band that slice can touch.
+ * hhsr_gather_bands: for n_frames <= 24 frames, sources raws/rs/covs/flows (HOST arrays of DEVICE pointers, peer-mapped
+ * over NVLink or local; covs or covs[f] may be NULL for the isotropic kernel) -> local full-size planes raws_local /
+ * rs_local / covs_local and flow copies flows_local.  The band of frame f is derived ON THE DEVICE from the vertical
+ * range of its flow over the tile rows covering LR rows [lr_begin, lr_end) and stored in extents[4 f .. 4 f + 3] =
+ * (row_lo, row_hi, covs_row_lo, covs_row_hi) (device int array, 16-byte aligned); only those rows are copied.  A frame
+ * whose source equals its destination (owned by this rank) is left in place. */
+int hhsr_gather_bands(const float *const *raws, const float *const *rs, const float *const *covs,
+                      const float *const *flows, float *const *raws_local, float *const *rs_local,
+                      float *const *covs_local, float *const *flows_local, int n_frames, int H, int W, int ny, int nx, int ts,
+                      int lr_begin, int lr_end, int *extents, hhsr_stream_t stream);
+/* hhsr_merge_accumulate_batch restricted to output rows [row_begin, row_end): num_rows / den_rows point at row
+ * `row_begin` (the caller may own only that slice: (row_end - row_begin) * Ws * 3 floats each). */
+int hhsr_merge_accumulate_rows(const float *const *raws, const float *const *flows, const float *const *covs,
+                               const float *const *rs, int K, int H, int W, int ny, int nx, int ts, float *num_rows,
+                               float *den_rows, int Hs, int Ws, double scale, const int *cfa_host, int iso, int flags,
+                               int row_begin, int row_end, hhsr_stream_t stream);
+/* hhsr_merge_ref on slice buffers: num_rows / den_rows point at row `row_begin`. */
+int hhsr_merge_ref_rows(const float *raw, int H, int W, const float *covs, float *num_rows, float *den_rows, int Hs, int Ws,
+                        double scale, const int *cfa_host, int iso, const double *acc_rob, int max_frame_count, int rad_max,
+                        double max_multiplier, int fuse_divide, int row_begin, int row_end, hhsr_stream_t stream);
+
 /* ---- frame-sharded runs (a B200 addition, the reference is single-GPU): the one reduction point of
  * the pipeline fused with merge_ref and divide.  peer_nums/peer_dens: HOST arrays of n_peers DEVICE pointers to the
  * ranks' private accumulators [Hs][Ws][3] (peer-mapped over NVLink, e.g. torch symmetric memory), summed in array
@@ -202,6 +226,13 @@ int hhsr_frame_count_denoise_gauss(const float *img, int Hs, int Ws, const doubl
                                    double sigma_max, double max_frame_count, float *out, hhsr_stream_t stream);
 int hhsr_frame_count_denoise_median(const float *img, int Hs, int Ws, const double *acc_rob, int H, int W, double scale,
                                     double radius_max, double max_frame_count, float *out, hhsr_stream_t stream);
+
+/* ---- noise curves (fast_monte_carlo.py:31-101 unitary_MC / regular_MC): for each of the n_levels
+ * brightness values (device float64 array) the Monte-Carlo means over n_patches pairs of noisy clipped 3x3 patches,
+ * diff_mean[l] = mean |mean(p1) - mean(p2)| and std_mean[l] = 0.5 mean(std(p1) + std(p2)) (device float64 arrays).
+ * Counter-based Philox generator: the result is a function of (seed, n_patches, levels) only. */
+int hhsr_noise_mc(const double *brightness, int n_levels, double alpha, double beta, int n_patches,
+                  unsigned long long seed, double *diff_mean, double *std_mean, hhsr_stream_t stream);
 
 /* ---- element-wise helpers (utils.py:62-120) */
 int hhsr_divide(float *num, const float *den, size_t n, hhsr_stream_t stream);

@@ -210,6 +210,9 @@ def test_pipeline_against_reference(name, batch):
         pytest.skip("the batched merge is compared on the main benchmark case")
     z, c, burst, cfg = get_case(name)
     tag = name if batch == 1 else name + "_batch%d" % batch
+    # the Ts-16 / Ts-64 bursts may hold a block-matching near-tie decided the other way (test_alignment_every_tile): one tile
+    # of such a frame then lands a pixel away, which moves the whole-array sums by more than rounding
+    sum_rtol = 1e-6 if name.startswith("bench") else 2e-5
     n_comp = c["n"] - 1
     seen = {"rob": 0, "kern": 0, "frames_merged": 0}
     worst = {"r": 0.0, "covs": 0.0}
@@ -222,11 +225,11 @@ def test_pipeline_against_reference(name, batch):
         d = crop_diff(r, z["r_f%d__crops" % f])
         worst["r"] = max(worst["r"], d)
         # r in [0, 1]; thresholded pixels (exact zeros) may flip where the reference sits on the threshold
-        check_summary(tag, "r_f%d" % f, r, z["r_f%d__sum" % f], sum_rtol=1e-6, zero_slack=max(8, int(2e-6 * r.numel())))
+        check_summary(tag, "r_f%d" % f, r, z["r_f%d__sum" % f], sum_rtol=sum_rtol, zero_slack=max(8, int(2e-6 * r.numel())))
         return r
 
-    def kern(img, config):
-        covs = saved["estimate_kernels"](img, config)
+    def kern(img, config, **kw):
+        covs = saved["estimate_kernels"](img, config, **kw)
         seen["kern"] += 1
         k = seen["kern"]
         d = crop_diff(covs.reshape(*covs.shape[:2], 4), z["covs_%d__crops" % k].reshape(9, *z["covs_%d__crops" % k].shape[1:3], 4))
@@ -242,8 +245,8 @@ def test_pipeline_against_reference(name, batch):
                 dd = crop_diff(den, z["den_%s__crops" % key], rel_floor=1.0)
                 record(tag, "num_den_%s_crops_rel" % key, [dn, dd])
                 assert dn < 5e-5 and dd < 5e-5      # float32 weights on flows that differ by a few 1e-6 px
-                check_summary(tag, "num_" + key, num, z["num_%s__sum" % key], zero_slack=int(1e-5 * num.numel()))
-                check_summary(tag, "den_" + key, den, z["den_%s__sum" % key], zero_slack=int(1e-5 * num.numel()))
+                check_summary(tag, "num_" + key, num, z["num_%s__sum" % key], sum_rtol=sum_rtol, zero_slack=int(1e-5 * num.numel()))
+                check_summary(tag, "den_" + key, den, z["den_%s__sum" % key], sum_rtol=sum_rtol, zero_slack=int(1e-5 * num.numel()))
 
     def merge(comp, al, covs, r, num, den, cfa, config, init=False):
         saved["merge"](comp, al, covs, r, num, den, cfa, config, init=init)
@@ -269,7 +272,7 @@ def test_pipeline_against_reference(name, batch):
     d = crop_diff(out, z["out__crops"])
     record(tag, "out_crops_max_abs", d)
     assert d < 1e-4
-    check_summary(tag, "out", out, z["out__sum"], zero_slack=8)
+    check_summary(tag, "out", out, z["out__sum"], sum_rtol=sum_rtol, zero_slack=8)
     acc = dbg["accumulated robustness"]
     assert crop_diff(acc, z["acc_rob__crops"]) < 2e-5 * n_comp
-    check_summary(tag, "acc_rob", acc, z["acc_rob__sum"], zero_slack=max(8, int(2e-6 * acc.numel())))
+    check_summary(tag, "acc_rob", acc, z["acc_rob__sum"], sum_rtol=sum_rtol, zero_slack=max(8, int(2e-6 * acc.numel())))

@@ -523,9 +523,11 @@ def test_merge_init_equals_accumulate_into_zeros(stage, scale):
 
 
 def test_process_on_burst_archives(tmp_path):
-    """process() (super_resolution.py:203-360 minus DNG I/O and the CPU ISP): a float32 archive and the same burst as
-    uint16 sensor counts give the same image; the config is enriched like the reference does (exif, noise curves,
-    SNR-derived parameters)."""
+    """process() (super_resolution.py:203-360 minus DNG I/O; post-processing switched off here, tests/test_post.py covers
+    it): a float32 archive and the same burst as uint16 sensor counts give the same image; the config is enriched like the
+    reference does (exif, noise curves, SNR-derived parameters).  Also `tile_size: SNR_based`, the reference's default:
+    this well-exposed burst selects Ts 16 (params.py:62-67), whose L1 level is rint(flow) here — equal to
+    main() with the tile size given explicitly."""
     import hhsr_oracle as O
     from handheld_super_resolution import process
     from handheld_super_resolution.config import load_config
@@ -541,7 +543,7 @@ def test_process_on_burst_archives(tmp_path):
     np.savez(tmp_path / "u16.npz", burst=counts, black_levels=np.asarray(black), white_level=white, **common)
     outs = []
     for name in ("f32.npz", "u16.npz"):
-        cfg = load_config(overrides={"scale": 2, "block_matching": {"tuning": {"tile_size": 32}}})
+        cfg = load_config(overrides={"scale": 2, "block_matching": {"tuning": {"tile_size": 32}}, "postprocessing": {"enabled": False}})
         img, dbg = process(str(tmp_path / name), cfg)
         assert img.shape == (1408, 1472, 3) and img.dtype == np.float32
         assert cfg.exif.cfa_pattern == CFA and len(cfg.noise_model.std_curve) == 1001
@@ -549,6 +551,14 @@ def test_process_on_burst_archives(tmp_path):
         outs.append(img)
     assert np.array_equal(np.nan_to_num(outs[0]), np.nan_to_num(outs[1]))
     assert np.isfinite(outs[0]).mean() > 0.999 and 0.05 < np.nanmean(outs[0]) < 0.95
+    # the reference's default: tile size chosen from the SNR
+    from handheld_super_resolution import main
+    cfg = load_config(overrides={"scale": 2, "postprocessing": {"enabled": False}})
+    assert cfg.block_matching.tuning.tile_size == "SNR_based"
+    img, _ = process(str(tmp_path / "f32.npz"), cfg)
+    assert cfg.block_matching.tuning.tile_size == 16 and cfg.block_matching.tuning.tile_sizes == [16, 16, 16, 8]
+    want, _ = main(fburst[0], fburst[1:], cfg)
+    assert np.array_equal(img, host(want), equal_nan=True)
 
 
 def test_divide_and_add():
@@ -711,3 +721,48 @@ def test_properties_full_size():
     n2, d2 = torch.zeros(shape, device="cuda"), torch.zeros(shape, device="cuda")
     MG.merge(raw, flow, covs, r1 + r2, n2, d2, CFA, cfg)
     assert (n1 - n2).abs().max().item() < 2e-6 and (d1 - d2).abs().max().item() < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ noise curves
+def test_noise_curves_gpu_monte_carlo():
+    """hhsr_noise_mc (seeded Philox Monte-Carlo, one CTA per brightness level) behind noise_model.run_fast_MC, against
+    the reference's own curves data/noise_model_{std,diff}_ISO_100.npy.  Those are themselves Monte-Carlo estimates
+    from 1e5 patch pairs (relative standard error ~0.05 % on sigma, ~0.24 % on d per level, carried into the
+    interpolated middle of the curves), so the comparison is statistical: 5 standard errors of the reference."""
+    from handheld_super_resolution.noise_model import regular_MC, regular_MC_numpy, run_fast_MC
+    alpha, beta = 1.80710882e-4, 3.1937599182128e-6
+    s1, d1 = run_fast_MC(alpha, beta, seed=0, n_patches=400000)
+    s2, d2 = run_fast_MC(alpha, beta, seed=0, n_patches=400000)
+    assert np.array_equal(s1, s2) and np.array_equal(d1, d2) and s1.shape == (1001,)      # reproducible
+    s3, d3 = run_fast_MC(alpha, beta, seed=1, n_patches=400000)
+    assert not np.array_equal(d1, d3)
+    std, diff = curves()
+    es, ed = np.abs(s1 - std) / std, np.abs(d1 - diff) / diff
+    record("noise_curves_rel_err_vs_reference", {"sigma_max": float(es.max()), "d_max": float(ed.max()),
+                                                 "sigma_mean": float(es.mean()), "d_mean": float(ed.mean())})
+    assert es.max() < 0.004 and ed.max() < 0.015
+    # the estimator itself, level by level, against NumPy on clipped and unclipped brightness levels (independent random
+    # numbers: 5 standard errors of the two estimates)
+    b = np.array([0.0, 0.001, 0.003, 0.01, 0.2, 0.7, 0.995, 0.999, 1.0])
+    sg, dg = regular_MC(b, alpha, beta, seed=3, n_patches=400000)
+    sn, dn = regular_MC_numpy(b, alpha, beta, seed=3, n_patches=400000)
+    ok = sn > 0
+    assert np.all(np.abs(sg[ok] - sn[ok]) / sn[ok] < 0.003) and np.all(np.abs(dg[ok] - dn[ok]) / dn[ok] < 0.012)
+    # closed form where nothing clips: d = E|N(0, 2 sigma^2 / 9)| = sigma * sqrt(4 / (9 pi))
+    sig = np.sqrt(alpha * 0.5 + beta)
+    sg, dg = regular_MC(np.array([0.5]), alpha, beta, seed=5, n_patches=1000000)
+    assert abs(dg[0] / (sig * np.sqrt(4 / (9 * np.pi))) - 1) < 0.004
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 1
+def test_main_against_reference_main_under_cudasim_config1():
+    """BASELINE.json config 1 (2 x 256 x 256, scale 1): main() against the output of the reference's own main() run under
+    NUMBA_ENABLE_CUDASIM=1 in the build container (1910 s on 8 host cores; tests/golden/config1_cudasim.npz)."""
+    from handheld_super_resolution import main
+    from test_oracle_golden import check_config1, config1_cfg
+    z = load("config1_cudasim.npz")
+    cfg = config1_cfg(attr_cfg, z["burst"])
+    cfg.debug = True
+    out, dbg = main(z["burst"][0], z["burst"][1:], cfg)
+    worst, n_over = check_config1(host(out), dbg["flow"][0], dbg["robustness"][0], z)
+    record("config1_cudasim_out", {"max_abs": worst, "pixels_over_1e-4": n_over})

@@ -127,10 +127,12 @@ def test_sanitize_config():
         sanitize_config(cfg_for(block_matching={"tuning": {"flow_upscale_mode": "cubic"}}), (3000, 4000))
 
 
-def test_noise_curves_seeded_and_close_to_reference():
-    from handheld_super_resolution.noise_model import run_fast_MC
-    s1, d1 = run_fast_MC(1.80710882e-4, 3.1937599182128e-6, seed=0, n_patches=20000)
-    s2, d2 = run_fast_MC(1.80710882e-4, 3.1937599182128e-6, seed=0, n_patches=20000)
+def test_noise_curve_host_logic_close_to_reference():
+    """run_fast_MC's host part (non-linearity bounds, placement of the Monte-Carlo levels, interpolation in between,
+    fast_monte_carlo.py:157-230) with the NumPy estimator standing in for the device kernel (tested in test_gpu_parity)."""
+    from handheld_super_resolution.noise_model import regular_MC_numpy, run_fast_MC
+    s1, d1 = run_fast_MC(1.80710882e-4, 3.1937599182128e-6, seed=0, n_patches=20000, mc=regular_MC_numpy)
+    s2, d2 = run_fast_MC(1.80710882e-4, 3.1937599182128e-6, seed=0, n_patches=20000, mc=regular_MC_numpy)
     assert np.array_equal(s1, s2) and np.array_equal(d1, d2) and s1.shape == (1001,)
     std, diff = curves()          # the reference's data/noise_model_*_ISO_100.npy
     assert np.abs(s1 - std).max() / std.max() < 0.03 and np.abs(d1 - diff).max() / diff.max() < 0.06
@@ -152,6 +154,19 @@ def test_frame_sharding():
         sizes = [len(p) for p in parts]
         assert max(sizes) - min(sizes) <= 1
     assert [len(shard_frames(19, r, 8)) for r in range(8)] == [3, 3, 3, 2, 2, 2, 2, 2]
+
+
+def test_row_slices_of_the_row_sharded_merge():
+    from handheld_super_resolution.distributed import equal_row_slices, p2p_row_slices
+    for Hs, world in [(6000, 8), (6000, 2), (9000, 8), (12288, 4), (100, 3), (24, 8), (8, 8), (7, 2)]:
+        for sl in (equal_row_slices(Hs, world), p2p_row_slices(Hs, world)):
+            assert len(sl) == world and sl[0][0] == 0 and sl[-1][1] == Hs
+            assert all(sl[i][1] == sl[i + 1][0] for i in range(world - 1)) and all(b >= a for a, b in sl)
+        sl = equal_row_slices(Hs, world)
+        assert all(a % 8 == 0 for a, _ in sl)                       # cuts on the 8-row blocks of the merge kernels
+        if Hs >= 8 * world:
+            sizes = [b - a for a, b in sl]
+            assert min(sizes) > 0 and max(sizes) - min(sizes) <= 8 + Hs % 8
 
 
 def test_raw_normalisation_host_matches_reference_loop():

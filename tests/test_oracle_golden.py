@@ -182,3 +182,36 @@ def test_cudasim_cases():
         assert maxdiff(gx, c["ica%d_gx" % t]) < 1e-6 and reldiff(hess, c["ica%d_hess" % t], floor=1.0) < 1e-5
         out = O.ica(c["ica%d_ref" % t], gx, gy, c["ica%d_hess" % t], c["ica%d_mov" % t], c["ica%d_flow0" % t], t, 3)
         assert maxdiff(out, c["ica%d_flow" % t]) < 1e-4
+
+
+def config1_cfg(maker, burst):
+    """BASELINE config 1 exactly as baseline/run_reference_cudasim.py builds it: scale 1, Ts 32, factors [1,2,2,2],
+    metrics [L1,L2,L2,L2], radii [1,4,4,4], SNR-derived merge constants (process() semantics)."""
+    from handheld_super_resolution.config import load_config
+    from handheld_super_resolution.params import update_snr_config
+    std, _ = curves()
+    b = float(np.mean(burst[0]))
+    full = load_config(overrides={"scale": 1, "block_matching": {"tuning": {"tile_size": 32}}})
+    update_snr_config(full, b / std[round(1000 * b)])
+    mt = full.merging.tuning
+    return maker(scale=1, tile_size=32, tile_sizes=[32, 32, 32, 16], factors=[1, 2, 2, 2], search_radii=[1, 4, 4, 4],
+                 metrics=["L1", "L2", "L2", "L2"], k_detail=mt.k_detail, k_denoise=mt.k_denoise, D_th=mt.D_th, D_tr=mt.D_tr)
+
+
+def check_config1(out, flow, r, z):
+    """Whole-pipeline comparison with the reference's OWN main() run under the Numba simulator (BASELINE config 1).  The
+    simulator evaluates kernels with NumPy scalar semantics (float32 op Python-float stays float32) where compiled Numba
+    promotes to float64, hence a handful of pixels (8 of 196 590 for the oracle) differ by up to ~1.4e-3."""
+    assert np.abs(flow - z["flows"][0]).max() < 1e-5
+    assert np.abs(r - z["robs"][0]).max() < 5e-5
+    assert np.array_equal(np.isnan(out), np.isnan(z["out"]))
+    m = np.isfinite(out)
+    d = np.abs(out[m].astype(np.float64) - z["out"][m])
+    assert np.percentile(d, 99.9) < 5e-5 and d.max() < 5e-3 and (d > 1e-4).sum() <= 40
+    return float(d.max()), int((d > 1e-4).sum())
+
+
+def test_oracle_against_reference_main_under_cudasim_config1():
+    z = load("config1_cudasim.npz")
+    out, dbg = O.main(z["burst"][0], z["burst"][1:], config1_cfg(plain_cfg, z["burst"]))
+    check_config1(out, dbg["flow"][0], dbg["robustness"][0], z)
