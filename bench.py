@@ -114,11 +114,15 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def merge_algorithmic_bytes(H, W, scale, ny, nx, K=1, init=False):
+def merge_algorithmic_bytes(H, W, scale, ny, nx, K=1, init=False, finish=False):
     """SURVEY section 8d / DESIGN.md, one merge launch over K comp frames: ONE pass over num+den (24 B per HR pixel
     written, and read as well unless the launch initialises them) + per frame raw, r, covariances (4 + 4 + 16/4 = 12 B
-    per LR pixel) and the tile flow:  B_batch(K) = HR*24*(1 + [not init]) + K*(LR*12 + tiles*8)  — never K * B_frame."""
+    per LR pixel) and the tile flow:  B_batch(K) = HR*24*(1 + [not init]) + K*(LR*12 + tiles*8)  — never K * B_frame.
+    A finishing launch (last batch fused with merge_ref + divide) writes the 12 B per HR pixel of the image instead of
+    num + den and also reads the reference frame and its covariances (8 B per LR pixel)."""
     hs, ws = round(scale * H), round(scale * W)
+    if finish:
+        return hs * ws * (12 + (0 if init else 24)) + K * (H * W * 12 + ny * nx * 8) + H * W * 8
     return hs * ws * 24 * (1 if init else 2) + K * (H * W * 12 + ny * nx * 8)
 
 
@@ -316,14 +320,14 @@ def run_cuda_arm(args, wl, wl_name):
         e0.record()
         orig_merge(*a, **k)
         e1.record()
-        merge_events.append((1, bool(k.get("init")), e0, e1))
+        merge_events.append((1, bool(k.get("init")), False, e0, e1))
 
     def timed_merge_batch(comps, *a, **k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         orig_merge_batch(comps, *a, **k)
         e1.record()
-        merge_events.append((len(comps), bool(k.get("init")), e0, e1))
+        merge_events.append((len(comps), bool(k.get("init")), k.get("finish") is not None, e0, e1))
     SR.merge, SR.merge_batch = timed_merge, timed_merge_batch
     batch = args.merge_batch if args.merge_batch > 0 else SR.MERGE_BATCH     # 0: automatic (main() decides per call)
     SR.MERGE_BATCH = batch
@@ -331,6 +335,34 @@ def run_cuda_arm(args, wl, wl_name):
     def step_resident():
         out, _ = main_sharded(burst_dev[0], burst_dev[1:], cfg)
         return out
+
+    out8_hosts = [torch.empty((hs, ws, 3), dtype=torch.uint8).pin_memory() for _ in range(2)] if world == 1 else None
+    post_cfg = cfg.postprocessing
+
+    def step_e2e_post(pipelined=True):
+        """What process() does on this path end to end (SURVEY 8f ranks 1 + 2): uint16 sensor counts in (480 MB),
+        main(), the reference's default post-process (unsharp mask + gamma) and uint8 quantisation ON THE DEVICE, 144 MB
+        out instead of 576 MB of float32."""
+        from handheld_super_resolution import raw2rgb
+        out, _ = SR.main(burst_u16[0], burst_u16[1:], cfg_u16)
+        img8 = raw2rgb.postprocess(None, out, post_cfg.do_color_correction, post_cfg.do_tonemapping, post_cfg.do_gamma_correction,
+                                   post_cfg.sharpening, post_cfg.do_devignetting, None, output_dtype="uint8")
+        k = d2h_state["k"] % 2
+        d2h_state["k"] += 1
+        if d2h_state["events"][k] is not None:
+            d2h_state["events"][k].synchronize()
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(d2h_stream if pipelined else torch.cuda.current_stream()):
+            if pipelined:
+                d2h_stream.wait_event(ready)
+            out8_hosts[k].copy_(img8, non_blocking=True)
+            img8.record_stream(torch.cuda.current_stream())
+            done = torch.cuda.Event()
+            done.record()
+        d2h_state["events"][k] = done
+        if not pipelined:
+            done.synchronize()
 
     def step_e2e(pipelined=True, u16=False):
         """Host burst in, host image out.  The D2H of the 48 MP result runs on its own stream into one of two pinned
@@ -394,7 +426,7 @@ def run_cuda_arm(args, wl, wl_name):
     launches0 = _lib.launch_count
     ms_res, t0, t1 = timed(step_resident, args.steps)
     launches = (_lib.launch_count - launches0)
-    merge_launches = [(K, init, a.elapsed_time(b)) for K, init, a, b in merge_events]
+    merge_launches = [(K, init, fin, a.elapsed_time(b)) for K, init, fin, a, b in merge_events]
     merge_events.clear()
     # the reference's launch granularity (one comp frame per pass over the accumulators) for comparison: a few steps
     # with the batching switched off; its read-modify-write launches are the kernel round 1 reported
@@ -404,19 +436,27 @@ def run_cuda_arm(args, wl, wl_name):
         step_resident()
         merge_events.clear()
         timed(step_resident, 2)
-        per_frame_ms = [a.elapsed_time(b) for K, init, a, b in merge_events if not init]
+        per_frame_ms = [a.elapsed_time(b) for K, init, fin, a, b in merge_events if not init and not fin]
         merge_events.clear()
         SR.MERGE_BATCH = batch
     if args.no_e2e:        # profiling runs (ncu replays every launch): the resident step only
         ms_e2e = ms_lat = ms_u16 = float("nan")
+        ms_post = ms_post_lat = None
         t2 = t1
     else:
         for _ in range(2):
             step_e2e()
         ms_e2e, _, t2 = timed(step_e2e, args.steps)
         ms_lat, _, t2 = timed(lambda: step_e2e(pipelined=False), max(2, args.steps // 2))   # one burst at a time, host-synchronous
-        step_e2e(u16=True)
+        for _ in range(2):
+            step_e2e(u16=True)
         ms_u16, _, t2 = timed(lambda: step_e2e(u16=True), args.steps)
+        ms_post = ms_post_lat = None
+        if world == 1:
+            for _ in range(2):
+                step_e2e_post()
+            ms_post, _, t2 = timed(step_e2e_post, args.steps)
+            ms_post_lat, _, t2 = timed(lambda: step_e2e_post(pipelined=False), max(2, args.steps // 2))
     clocks = sampler.stop(t0, t2) if rank == 0 else None
     SR.merge, SR.merge_batch = orig_merge, orig_merge_batch
     alloc = torch.cuda.memory_stats()
@@ -447,40 +487,40 @@ def run_cuda_arm(args, wl, wl_name):
     names = args.extra_workloads
     names = (["13x12MP_s3", "20x50MP_s2"] if world >= 8 else []) if names == "auto" else [x for x in names.split(",") if x and x != "none"]
     if names:
-        del burst_dev, burst_host, burst_u16, out_hosts
-        from handheld_super_resolution import distributed as D
-        D.RowShardedMerge._cache.clear(), D.P2PReduce._cache.clear()
+        del burst_dev, burst_host, burst_u16      # (symmetric-memory buffers of the main workload stay mapped: a few GB)
         torch.cuda.empty_cache()
     for name in names:
         w2 = WORKLOADS[name]
-        b2, _ = synth_burst(w2["n"], w2["H"], w2["W"], seed=0, device="cuda", as_numpy=False)
-        c2 = make_config(w2["scale"], w2["H"], w2["W"], b2[0].mean().item())
-        fn = lambda: main_sharded(b2[0], b2[1:], c2)      # noqa: E731
-        for _ in range(3):
-            fn()
-        ms2, _, _ = timed(fn, max(3, args.steps // 2))
-        mp = round(w2["scale"] * w2["H"]) * round(w2["scale"] * w2["W"]) / 1e6
-        extras.append({"workload": name, **w2, "ms_per_step": ms2, "value": mp / (ms2 * 1e-3), "unit": "MPix/s", "n_gpus": world,
-                       "note": "resident burst, same call and exchange mode as the main workload"})
-        del b2
-        from handheld_super_resolution import distributed as D
-        D.RowShardedMerge._cache.clear(), D.P2PReduce._cache.clear()
-        torch.cuda.empty_cache()
+        try:
+            b2, _ = synth_burst(w2["n"], w2["H"], w2["W"], seed=0, device="cuda", as_numpy=False)
+            c2 = make_config(w2["scale"], w2["H"], w2["W"], b2[0].mean().item())
+            fn = lambda: main_sharded(b2[0], b2[1:], c2)      # noqa: E731
+            for _ in range(3):
+                fn()
+            ms2, _, _ = timed(fn, max(3, args.steps // 2))
+            mp = round(w2["scale"] * w2["H"]) * round(w2["scale"] * w2["W"]) / 1e6
+            extras.append({"workload": name, **w2, "ms_per_step": ms2, "value": mp / (ms2 * 1e-3), "unit": "MPix/s", "n_gpus": world,
+                           "note": "resident burst, same call and exchange mode as the main workload"})
+            del b2
+            torch.cuda.empty_cache()
+        except Exception as e:      # an extra must never cost the main line
+            extras.append({"workload": name, "error": repr(e)[:300]})
+            break
 
     if rank == 0:
         out_mpix = hs * ws / 1e6
         peak, peak_src = measured_peak_gbs()
         ny, nx = -(-H // 32), -(-W // 32)
         # roofline of the merge launches of the timed steps: algorithmic bytes B_batch(K) of every launch / its duration
-        alg_total = sum(merge_algorithmic_bytes(H, W, scale, ny, nx, K, init) for K, init, _ in merge_launches)
-        ms_total = sum(ms for _, _, ms in merge_launches)
-        frames_total = sum(K for K, _, _ in merge_launches)
+        alg_total = sum(merge_algorithmic_bytes(H, W, scale, ny, nx, K, init, fin) for K, init, fin, _ in merge_launches)
+        ms_total = sum(ms for _, _, _, ms in merge_launches)
+        frames_total = sum(K for K, _, _, _ in merge_launches)
         achieved = alg_total / (ms_total * 1e-3) / 1e9 if ms_total > 0 else float("nan")
         n_launch = max(len(merge_launches), 1)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "merge_traffic_bytes.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("%s_batch%d" % (wl_name, max(K for K, _, _ in merge_launches) if merge_launches else 0))
+            traffic = json.load(open(tp)).get("%s_batch%d" % (wl_name, max(K for K, _, _, _ in merge_launches) if merge_launches else 0))
         alg1 = merge_algorithmic_bytes(H, W, scale, ny, nx)
         pf_ms = float(np.mean(per_frame_ms)) if per_frame_ms else None
         line = {
@@ -502,18 +542,25 @@ def run_cuda_arm(args, wl, wl_name):
                     "single_burst_latency_ms": ms_lat, "single_burst_value": out_mpix / (ms_lat * 1e-3),
                     "uint16_raw": {"value": out_mpix / (ms_u16 * 1e-3), "ms_per_step": ms_u16,
                                    "h2d_bytes_per_step": int(n * H * W * 2),
-                                   "note": "same call fed with 14-bit sensor counts (uint16), normalised on the device"}},
+                                   "note": "same call fed with 14-bit sensor counts (uint16), normalised on the device"},
+                    "uint16_in_uint8_out": None if ms_post is None else {
+                        "value": out_mpix / (ms_post * 1e-3), "ms_per_step": ms_post, "single_burst_latency_ms": ms_post_lat,
+                        "h2d_bytes_per_step": int(n * H * W * 2), "d2h_bytes_per_step": int(hs * ws * 3),
+                        "note": "the process() path: uint16 sensor counts in, main(), the reference's default post-process (unsharp "
+                                "mask + gamma, raw2rgb.py:212-250) and uint8 quantisation on the device, uint8 image out"}},
             "gpu_launches": int(launches),
             "roofline": {"kernel": ("accumulate_pow2_batch_kernel (merge, up to %d comp frames per pass over the accumulators)"
-                                    % max(K for K, _, _ in merge_launches)) if frames_total > len(merge_launches)
+                                    % max(K for K, _, _, _ in merge_launches)) if frames_total > len(merge_launches)
                                    else "accumulate_pow2_kernel (merge, one comp frame per launch)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_total / n_launch, "avg_launch_ms": ms_total / n_launch,
                          "launches_timed": len(merge_launches), "frames_per_launch": frames_total / n_launch,
                          "ms_per_frame": ms_total / max(frames_total, 1),
-                         "accounting": "B_batch(K) = HR*24*(1 + [not init]) + K*(LR*12 + tiles*8) per launch (SURVEY 8d), "
-                                       "summed over every merge launch of the timed steps / summed CUDA-event durations",
+                         "accounting": "B_batch(K) = HR*24*(1 + [not init]) + K*(LR*12 + tiles*8) per launch (SURVEY 8d; the launch that "
+                                       "also merges the reference frame and divides writes HR*12 instead of HR*24 and reads LR*8 more), "
+                                       "summed over every merge launch of the timed steps / summed CUDA-event durations; ms_per_frame "
+                                       "counts the reference frame's merge + divide inside the finishing launch as part of its frames",
                          "note": "frame batching removes accumulator traffic: the kernel moves from the HBM roofline to the "
                                  "issue limit of the tap arithmetic, so the step gets faster while this fraction falls",
                          "per_frame_kernel": None if pf_ms is None else {

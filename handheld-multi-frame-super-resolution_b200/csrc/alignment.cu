@@ -165,92 +165,156 @@ __global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ re
     }
 }
 
-// Register-tiled variant for 32x32 tiles (the default tile size): each warp owns 4 tile rows, each lane one column
-// and keeps -2*ref for its 4 pixels in registers.  One window value read from shared memory then feeds up to 4
-// (row, vertical shift) pairs, cutting shared-memory traffic ~6x against bm_l2_kernel; per-lane partial SSDs of a group
-// of 3 horizontal shifts x all vertical shifts are transposed through shared memory and summed in a fixed order
-// (rows, then lanes, then warps), so equal windows give bit-equal sums and the first-minimum rule is preserved.
+// Register-tiled variant for 32x32 tiles (the default tile size), persistent over tiles.
+//   E(v,u) = S(v,u) + C(v,u),  S = sum of m^2 over the shifted window,  C = sum of m * (-2 ref).
+// C: each warp owns 4 tile rows, each lane one column and keeps -2*ref of its 4 pixels in registers; one window value read
+// from shared memory feeds up to 4 (row, vertical shift) pairs and every term is ONE float64 FMA.  Per-lane partials of a
+// group of 3 horizontal shifts x all vertical shifts are transposed through shared memory and summed in a fixed order
+// (rows, then lanes, then warps).  S: column sums of m^2 per vertical shift (32 FMAs each, fixed order), then 32 column
+// sums per shift — 14 % of the operations of C instead of one extra float64 add per term.  Both parts depend only on the
+// CONTENT of a shifted window, so equal windows (clamped borders) give bit-equal energies and the first-minimum rule is
+// preserved.  A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: while it searches one tile, the window and the
+// reference pixels of its next tile are already in flight (registers), so the global-memory latency that bounded the
+// one-tile-per-CTA version (long-scoreboard stalls, FP64 pipe 40 % busy) is off the critical path.
 template <int R>
-__global__ void __launch_bounds__(256) bm_l2_tiled32_kernel(const float *__restrict__ ref, int ref_w, const float *__restrict__ mov,
-                                                            int mov_h, int mov_w, float2 *__restrict__ flow, int nx) {
+__global__ void __launch_bounds__(256, 2) bm_l2_tiled32_kernel(const float *__restrict__ ref, int ref_w, const float *__restrict__ mov,
+                                                               int mov_h, int mov_w, float2 *__restrict__ flow, int nx, int ntiles) {
     constexpr int TS = 32, N = 2 * R + 1, SW = TS + 2 * R, RW = 4, UG = 3, NG = (N + UG - 1) / UG, NV = N * UG;
+    constexpr int NWIN = SW * SW, PF = (NWIN + 255) / 256;
     static_assert(NV <= 32, "search radius too large for the tiled kernel");
     extern __shared__ double bsm[];
-    double *s_win = bsm;                        // [SW][SW]
-    double *s_red = s_win + SW * SW;            // [8][NV][33]
+    double *s_win0 = bsm;                       // [2][SW][SW]
+    double *s_red = s_win0 + 2 * NWIN;          // [8][NV][33]
     double *s_part = s_red + 8 * NV * 33;       // [8][N*N]
-    double *s_err = s_part + 8 * N * N;         // [N*N]
-    const int tx = blockIdx.x, ty = blockIdx.y;
-    const float2 f = flow[(size_t)ty * nx + tx];
-    const int fx = (int)rintf(f.x), fy = (int)rintf(f.y);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int yy0 = warp; yy0 < SW; yy0 += 8) {
-        const int yy = min(max(ty * TS + fy - R + yy0, 0), mov_h - 1);
-        for (int xx0 = lane; xx0 < SW; xx0 += 32) {
-            const int xx = min(max(tx * TS + fx - R + xx0, 0), mov_w - 1);
-            s_win[yy0 * SW + xx0] = (double)__ldg(mov + (size_t)yy * mov_w + xx);
-        }
-    }
+    double *s_col = s_part + 8 * N * N;         // [N][SW]
+    double *s_S = s_col + N * SW;               // [N*N]
+    double *s_err = s_S + N * N;                // [N*N]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int yb = warp * RW;
-    double rf[RW];
+
+    // window sample `i` (row-major in the SW x SW window) of tile t with rounded flow (fx, fy): clamped read (:368-369)
+    auto win_load = [&](int t, int fx, int fy, int i) -> float {
+        const int yy0 = i / SW, xx0 = i - yy0 * SW;
+        const int ty = t / nx, tx = t - ty * nx;
+        const int yy = min(max(ty * TS + fy - R + yy0, 0), mov_h - 1), xx = min(max(tx * TS + fx - R + xx0, 0), mov_w - 1);
+        return __ldg(mov + (size_t)yy * mov_w + xx);
+    };
+    auto ref_load = [&](int t, int k) -> float {
+        const int ty = t / nx, tx = t - ty * nx;
+        return __ldg(ref + (size_t)(ty * TS + yb + k) * ref_w + tx * TS + lane);
+    };
+
+    int t = blockIdx.x, buf = 0;
+    float2 f = make_float2(0.f, 0.f);
+    float rfn[RW];
+    if (t < ntiles) {
+        f = flow[t];
+        const int fx = (int)rintf(f.x), fy = (int)rintf(f.y);                    // flow.round(), :352
+        for (int i = tid; i < NWIN; i += 256) s_win0[i] = (double)win_load(t, fx, fy, i);
 #pragma unroll
-    for (int k = 0; k < RW; ++k) rf[k] = -2.0 * (double)__ldg(ref + (size_t)(ty * TS + yb + k) * ref_w + tx * TS + lane);
+        for (int k = 0; k < RW; ++k) rfn[k] = ref_load(t, k);
+    }
     __syncthreads();
-    double *red = s_red + warp * (NV * 33);
-    for (int g = 0; g < NG; ++g) {
-        double acc[N][UG];
+    for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+        double *s_win = s_win0 + buf * NWIN;
+        double rf[RW];
 #pragma unroll
-        for (int v = 0; v < N; ++v)
+        for (int k = 0; k < RW; ++k) rf[k] = -2.0 * (double)rfn[k];
+        // next tile of this CTA: flow, window and reference pixels go in flight now and land in registers
+        const int tn = t + gridDim.x;
+        float2 fn = make_float2(0.f, 0.f);
+        float pf[PF];
+        if (tn < ntiles) {
+            fn = flow[tn];                                                        // tile tn is only ever written by this CTA
+            const int fx = (int)rintf(fn.x), fy = (int)rintf(fn.y);
 #pragma unroll
-            for (int uu = 0; uu < UG; ++uu) acc[v][uu] = 0.0;
-#pragma unroll
-        for (int rr = 0; rr < RW + N - 1; ++rr) {
-            double m[UG];
-#pragma unroll
-            for (int uu = 0; uu < UG; ++uu) {
-                const int u = g * UG + uu;
-                m[uu] = (u < N) ? s_win[(yb + rr) * SW + lane + u] : 0.0;
+            for (int q = 0; q < PF; ++q) {
+                const int i = tid + q * 256;
+                pf[q] = (i < NWIN) ? win_load(tn, fx, fy, i) : 0.f;
             }
 #pragma unroll
-            for (int k = 0; k < RW; ++k) {
-                const int v = rr - k;        // window row yb+rr is row (yb+k) displaced by v
-                if (v >= 0 && v < N) {
+            for (int k = 0; k < RW; ++k) rfn[k] = ref_load(tn, k);
+        }
+        // S, step 1: column sums of m^2 for every vertical shift
+        for (int c = tid; c < N * SW; c += 256) {
+            const int v = c / SW, X = c - v * SW;
+            const double *q = s_win + v * SW + X;
+            double a = 0.0;
+#pragma unroll 8
+            for (int y = 0; y < TS; ++y) a = fma(q[y * SW], q[y * SW], a);
+            s_col[c] = a;
+        }
+        // C: register-tiled cross term
+        double *red = s_red + warp * (NV * 33);
+        for (int g = 0; g < NG; ++g) {
+            double acc[N][UG];
 #pragma unroll
-                    for (int uu = 0; uu < UG; ++uu) acc[v][uu] = fma(m[uu], m[uu] + rf[k], acc[v][uu]);
+            for (int v = 0; v < N; ++v)
+#pragma unroll
+                for (int uu = 0; uu < UG; ++uu) acc[v][uu] = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < RW + N - 1; ++rr) {
+                double m[UG];
+#pragma unroll
+                for (int uu = 0; uu < UG; ++uu) {
+                    const int u = g * UG + uu;
+                    m[uu] = (u < N) ? s_win[(yb + rr) * SW + lane + u] : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < RW; ++k) {
+                    const int v = rr - k;        // window row yb+rr is row (yb+k) displaced by v
+                    if (v >= 0 && v < N) {
+#pragma unroll
+                        for (int uu = 0; uu < UG; ++uu) acc[v][uu] = fma(m[uu], rf[k], acc[v][uu]);
+                    }
                 }
             }
+#pragma unroll
+            for (int v = 0; v < N; ++v)
+#pragma unroll
+                for (int uu = 0; uu < UG; ++uu) red[(v * UG + uu) * 33 + lane] = acc[v][uu];
+            __syncwarp();
+            if (lane < NV) {
+                // four interleaved partial sums (a fixed order: equal windows still give bit-equal totals)
+                double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+                const double *q = red + lane * 33;
+#pragma unroll
+                for (int l = 0; l < 32; l += 4) e0 += q[l], e1 += q[l + 1], e2 += q[l + 2], e3 += q[l + 3];
+                const double e = (e0 + e1) + (e2 + e3);
+                const int v = lane / UG, u = g * UG + lane % UG;
+                if (u < N) s_part[warp * N * N + v * N + u] = e;
+            }
+            __syncwarp();
         }
+        __syncthreads();                        // s_col and s_part complete
+        if (tid < N * N) {
+            const int v = tid / N, u = tid - v * N;
+            const double *q = s_col + v * SW + u;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // S, step 2: the 32 column sums of this shift, fixed order
 #pragma unroll
-        for (int v = 0; v < N; ++v)
-#pragma unroll
-            for (int uu = 0; uu < UG; ++uu) red[(v * UG + uu) * 33 + lane] = acc[v][uu];
-        __syncwarp();
-        if (lane < NV) {
-            // four interleaved partial sums (a fixed order too: equal windows still give bit-equal totals) instead of one
-            // chain of 32 dependent float64 additions
-            double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
-            const double *q = red + lane * 33;
-#pragma unroll
-            for (int l = 0; l < 32; l += 4) e0 += q[l], e1 += q[l + 1], e2 += q[l + 2], e3 += q[l + 3];
-            const double e = (e0 + e1) + (e2 + e3);
-            const int v = lane / UG, u = g * UG + lane % UG;
-            if (u < N) s_part[warp * N * N + v * N + u] = e;
+            for (int x = 0; x < TS; x += 4) s0 += q[x], s1 += q[x + 1], s2 += q[x + 2], s3 += q[x + 3];
+            double e = 0.0;
+            for (int w = 0; w < 8; ++w) e += s_part[w * N * N + tid];
+            s_err[tid] = ((s0 + s1) + (s2 + s3)) + e;
         }
-        __syncwarp();
-    }
-    __syncthreads();
-    if (threadIdx.x < N * N) {
-        double e = 0.0;
-        for (int w = 0; w < 8; ++w) e += s_part[w * N * N + threadIdx.x];
-        s_err[threadIdx.x] = e;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int best = 0;
-        double be = s_err[0];
-        for (int s = 1; s < N * N; ++s)
-            if (s_err[s] < be) be = s_err[s], best = s;
-        flow[(size_t)ty * nx + tx] = make_float2(f.x + (float)(best % N - R), f.y + (float)(best / N - R));
+        // the prefetched window of the next tile goes into the other buffer (nobody reads it before the next barrier)
+        if (tn < ntiles) {
+            double *nw = s_win0 + (buf ^ 1) * NWIN;
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+                const int i = tid + q * 256;
+                if (i < NWIN) nw[i] = (double)pf[q];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int best = 0;
+            double be = s_err[0];
+            for (int sft = 1; sft < N * N; ++sft)
+                if (s_err[sft] < be) be = s_err[sft], best = sft;                // first minimum, torch.argmin
+            flow[t] = make_float2(f.x + (float)(best % N - R), f.y + (float)(best / N - R));
+        }
+        f = fn;
     }
 }
 
@@ -490,10 +554,12 @@ extern "C" int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const f
 #define HHSR_BMT(R)                                                                                                   \
     do {                                                                                                              \
         constexpr int N = 2 * R + 1, SW = 32 + 2 * R;                                                                 \
-        const size_t sm = (size_t)(SW * SW + 8 * N * 3 * 33 + 8 * N * N + N * N) * sizeof(double);                    \
+        const size_t sm = (size_t)(2 * SW * SW + 8 * N * 3 * 33 + 8 * N * N + N * SW + 2 * N * N) * sizeof(double);   \
         static std::atomic<unsigned long long> done{0};                                                               \
         ensure_dynamic_smem(bm_l2_tiled32_kernel<R>, done, sm);                                                       \
-        bm_l2_tiled32_kernel<R><<<grid, 256, sm, st>>>(ref, ref_w, mov, mov_h, mov_w, F2, nx);                         \
+        const int ntiles = nx * ny;                                                                                   \
+        const int ctas = ntiles < 148 * 2 ? ntiles : 148 * 2;       /* persistent: 2 CTAs per SM walk the tiles */    \
+        bm_l2_tiled32_kernel<R><<<ctas, 256, sm, st>>>(ref, ref_w, mov, mov_h, mov_w, F2, nx, ntiles);                 \
     } while (0)
         switch (radius) {
             case 1: HHSR_BMT(1); break;

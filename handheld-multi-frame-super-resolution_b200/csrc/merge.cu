@@ -599,11 +599,26 @@ __device__ __noinline__ void border_frame_sums(const MergeFrame *f, const MergeG
     }
 }
 
-template <bool ISO, int K, bool STORE>
+// FIN: the batch is the LAST one of the burst and the reference frame follows in the same pass — its window sums
+// (accumulate_ref, merge.py:82-233) are added to the register accumulators, the quotient num / den (utils.divide) is
+// formed and ONLY the finished image is written: num / den never return to HBM (48 B per HR pixel less than a separate
+// merge_ref pass, which is also one launch less).  Same per-pixel code and operation order as accumulate_ref_kernel with
+// fuse_divide, hence bit-identical to merge + merge_ref.
+struct RefFinish {
+    const float *raw, *covs;
+    float *out;       // [Hs][Ws][3], indexed like num
+};
+template <bool ISO>
+__device__ __forceinline__ bool ref_pixel(const float *__restrict__ raw, const float *__restrict__ covs, const MergeGeom &g, int ox,
+                                          int oy, const double *__restrict__ acc_rob, int max_frame_count, int rad_max,
+                                          float max_multiplier, float (&val)[3], float (&acc)[3]);
+
+template <bool ISO, int K, bool STORE, bool FIN>
 __global__ void __launch_bounds__(256, HHSR_MERGE_BATCH_MINBLOCKS) accumulate_pow2_batch_kernel(const __grid_constant__ MergeBatch b,
                                                                                             const __grid_constant__ MergeGeom g,
                                                                                             float *__restrict__ num,
-                                                                                            float *__restrict__ den) {
+                                                                                            float *__restrict__ den,
+                                                                                            const __grid_constant__ RefFinish fin) {
     constexpr int SH = K + 1, MASK = (1 << SH) - 1;
     constexpr float INV = 1.0f / (float)(1 << SH);
     const int hr_i = g.row_begin + blockIdx.y * blockDim.y + threadIdx.y;
@@ -639,6 +654,22 @@ __global__ void __launch_bounds__(256, HHSR_MERGE_BATCH_MINBLOCKS) accumulate_po
                 sink.d[q] = add_ftz(sink.d[q], tmp[24 + q / 3], tmp[12 + q]);
             }
         }
+    }
+    if (FIN) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float val[3], acc[3];
+            ref_pixel<ISO>(fin.raw, fin.covs, g, j0 + p, hr_i, nullptr, 0, 0, 0.f, val, acc);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float n_ = sink.n[3 * p + c] + val[c], d_ = sink.d[3 * p + c] + acc[c];     // accumulate_ref_kernel, fuse_divide
+                sink.n[3 * p + c] = n_ / d_;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            *reinterpret_cast<float4 *>(fin.out + base + 4 * q) = make_float4(sink.n[4 * q], sink.n[4 * q + 1], sink.n[4 * q + 2], sink.n[4 * q + 3]);
+        return;
     }
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -979,7 +1010,15 @@ static int pow2_fast_shift(const MergeGeom &g) {
 
 template <int K, bool STORE>
 static void launch_pow2(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso, dim3 grid, dim3 block,
-                        cudaStream_t st) {
+                        cudaStream_t st, const RefFinish *fin) {
+    if (fin != nullptr) {
+        if (iso)
+            accumulate_pow2_batch_kernel<true, K, STORE, true><<<grid, block, 0, st>>>(b, g, num, den, *fin);
+        else
+            accumulate_pow2_batch_kernel<false, K, STORE, true><<<grid, block, 0, st>>>(b, g, num, den, *fin);
+        return;
+    }
+    const RefFinish none{nullptr, nullptr, nullptr};
     if (b.K == 1 && g.row_begin == 0 && g.row_end == g.Hs) {
         if (iso)
             accumulate_pow2_kernel<true, K, STORE><<<grid, block, 0, st>>>(b.f[0], g, num, den);
@@ -987,25 +1026,26 @@ static void launch_pow2(const MergeBatch &b, const MergeGeom &g, float *num, flo
             accumulate_pow2_kernel<false, K, STORE><<<grid, block, 0, st>>>(b.f[0], g, num, den);
     } else {
         if (iso)
-            accumulate_pow2_batch_kernel<true, K, STORE><<<grid, block, 0, st>>>(b, g, num, den);
+            accumulate_pow2_batch_kernel<true, K, STORE, false><<<grid, block, 0, st>>>(b, g, num, den, none);
         else
-            accumulate_pow2_batch_kernel<false, K, STORE><<<grid, block, 0, st>>>(b, g, num, den);
+            accumulate_pow2_batch_kernel<false, K, STORE, false><<<grid, block, 0, st>>>(b, g, num, den, none);
     }
 }
 
 template <bool STORE>
 static int launch_accumulate(const MergeBatch &b, const MergeGeom &g, float *num, float *den, int iso, bool generic,
-                             cudaStream_t st) {
+                             cudaStream_t st, const RefFinish *fin = nullptr) {
     dim3 block(32, 8);
     const int k = generic ? -1 : pow2_fast_shift(g);
     const int rows = g.row_end - g.row_begin;
     if (k >= 0) {
         dim3 grid(ceil_div(g.Ws, 32 * 4), ceil_div(rows, 8));
-        if (k == 0) launch_pow2<0, STORE>(b, g, num, den, iso, grid, block, st);
-        if (k == 1) launch_pow2<1, STORE>(b, g, num, den, iso, grid, block, st);
-        if (k == 2) launch_pow2<2, STORE>(b, g, num, den, iso, grid, block, st);
+        if (k == 0) launch_pow2<0, STORE>(b, g, num, den, iso, grid, block, st, fin);
+        if (k == 1) launch_pow2<1, STORE>(b, g, num, den, iso, grid, block, st, fin);
+        if (k == 2) launch_pow2<2, STORE>(b, g, num, den, iso, grid, block, st, fin);
         return launch_status("merge_accumulate");
     }
+    if (fin != nullptr) return unsupported("the fused finish needs the power-of-two fast path (scale 1, 2 or 4, output width a multiple of 4)");
     if (g.Ws % 4 == 0)
         launch_accumulate_vec<4, STORE>(b, g, num, den, iso, dim3(ceil_div(g.Ws, 32 * 4), ceil_div(rows, 8)), block, st);
     else
@@ -1019,8 +1059,10 @@ using namespace hhsr;
 
 static int merge_frames(const float *const *raws, const float *const *flows, const float *const *covs, const float *const *rs,
                         int K, int H, int W, int ny, int nx, int ts, float *num, float *den, int Hs, int Ws, double scale,
-                        const int *cfa_host, int iso, int flags, int row_begin, int row_end, hhsr_stream_t stream) {
+                        const int *cfa_host, int iso, int flags, int row_begin, int row_end, hhsr_stream_t stream,
+                        const RefFinish *fin = nullptr) {
     HHSR_REQUIRE((flags & ~(HHSR_MERGE_INIT | HHSR_MERGE_GENERIC)) == 0, "unknown merge flag");
+    HHSR_REQUIRE(fin == nullptr || !(flags & HHSR_MERGE_GENERIC), "the fused finish runs on the fast path only");
     HHSR_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= Hs, "row range must satisfy 0 <= begin < end <= Hs");
     const bool generic = (flags & HHSR_MERGE_GENERIC) != 0;
     HHSR_REQUIRE(raws && flows && rs && K > 0, "null frame list");
@@ -1031,6 +1073,13 @@ static int merge_frames(const float *const *raws, const float *const *flows, con
     g.row_begin = row_begin, g.row_end = row_end;
     // num / den point at row `row_begin` (a caller may own only that slice); the kernels index rows absolutely
     num -= (size_t)row_begin * Ws * 3, den -= (size_t)row_begin * Ws * 3;
+    RefFinish finish{nullptr, nullptr, nullptr};
+    if (fin != nullptr) {
+        HHSR_REQUIRE(fin->raw && fin->out && (iso || fin->covs), "fused finish: null reference frame / covariances / output");
+        HHSR_REQUIRE((uintptr_t)fin->out % 16 == 0 && (iso || (uintptr_t)fin->covs % 16 == 0), "fused finish: misaligned buffers");
+        HHSR_REQUIRE(pow2_fast_shift(g) >= 0, "the fused finish needs the power-of-two fast path (scale 1, 2 or 4, output width % 4 == 0)");
+        finish = RefFinish{fin->raw, iso ? nullptr : fin->covs, fin->out - (size_t)row_begin * Ws * 3};
+    }
     for (int k0 = 0; k0 < K; k0 += kMaxBatch) {
         MergeBatch b;
         b.K = (K - k0 < kMaxBatch) ? K - k0 : kMaxBatch;
@@ -1041,8 +1090,9 @@ static int merge_frames(const float *const *raws, const float *const *flows, con
         }
         // only the first chunk of an initialising call stores; later chunks accumulate onto it
         const bool store = (flags & HHSR_MERGE_INIT) != 0 && k0 == 0;
-        const int e = store ? launch_accumulate<true>(b, g, num, den, iso, generic, (cudaStream_t)stream)
-                            : launch_accumulate<false>(b, g, num, den, iso, generic, (cudaStream_t)stream);
+        const RefFinish *f = (fin != nullptr && k0 + kMaxBatch >= K) ? &finish : nullptr;     // the last chunk finishes
+        const int e = store ? launch_accumulate<true>(b, g, num, den, iso, generic, (cudaStream_t)stream, f)
+                            : launch_accumulate<false>(b, g, num, den, iso, generic, (cudaStream_t)stream, f);
         if (e) return e;
     }
     return 0;
@@ -1061,6 +1111,16 @@ extern "C" int hhsr_merge_accumulate_rows(const float *const *raws, const float 
                                           int iso, int flags, int row_begin, int row_end, hhsr_stream_t stream) {
     return merge_frames(raws, flows, covs, rs, K, H, W, ny, nx, ts, num_rows, den_rows, Hs, Ws, scale, cfa_host, iso, flags,
                         row_begin, row_end, stream);
+}
+
+extern "C" int hhsr_merge_finish_rows(const float *const *raws, const float *const *flows, const float *const *covs,
+                                      const float *const *rs, int K, int H, int W, int ny, int nx, int ts, float *num_rows,
+                                      float *den_rows, int Hs, int Ws, double scale, const int *cfa_host, int iso, int flags,
+                                      int row_begin, int row_end, const float *ref_raw, const float *ref_covs, float *out_rows,
+                                      hhsr_stream_t stream) {
+    RefFinish fin{ref_raw, ref_covs, out_rows};
+    return merge_frames(raws, flows, covs, rs, K, H, W, ny, nx, ts, num_rows, den_rows, Hs, Ws, scale, cfa_host, iso, flags,
+                        row_begin, row_end, stream, &fin);
 }
 
 extern "C" int hhsr_merge_accumulate(const float *raw, int H, int W, const float *flow, int ny, int nx, int ts,

@@ -20,27 +20,39 @@ struct GatherList {
 };
 
 // ext[f] = (lo, hi, covs_lo, covs_hi)
-__global__ void __launch_bounds__(256) band_extents_kernel(const __grid_constant__ GatherList l, int ny, int nx, int ts, int H, int lr0,
-                                                           int lr1, int4 *__restrict__ ext) {
+constexpr int kExtThreads = 1024;
+__global__ void __launch_bounds__(kExtThreads) band_extents_kernel(const __grid_constant__ GatherList l, int ny, int nx, int ts, int H, int lr0,
+                                                                   int lr1, int4 *__restrict__ ext) {
     const int f = blockIdx.x;
     const float2 *src = reinterpret_cast<const float2 *>(l.flow[f]);
     float2 *dst = reinterpret_cast<float2 *>(l.flow_l[f]);
     const int py0 = lr0 / ts, py1 = min((lr1 - 1) / ts, ny - 1);
     float mn = INFINITY, mx = -INFINITY;
-    for (int i = threadIdx.x; i < ny * nx; i += blockDim.x) {
-        const float2 v = src[i];
-        if (dst != src) dst[i] = v;
-        const int py = i / nx;
-        if (py >= py0 && py <= py1) mn = fminf(mn, v.y), mx = fmaxf(mx, v.y);
+    const int n = ny * nx;
+    // four independent (remote) loads in flight per thread: the NVLink round trip is paid ~n / 4096 times, not n / 256
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * kExtThreads) {
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kExtThreads;
+            v[u] = (i < n) ? src[i] : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kExtThreads;
+            if (i >= n) continue;
+            if (dst != src) dst[i] = v[u];
+            const int py = i / nx;
+            if (py >= py0 && py <= py1) mn = fminf(mn, v[u].y), mx = fmaxf(mx, v[u].y);
+        }
     }
-    __shared__ float smn[8], smx[8];
+    __shared__ float smn[kExtThreads / 32], smx[kExtThreads / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)), mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) smn[threadIdx.x >> 5] = mn, smx[threadIdx.x >> 5] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; ++k) mn = fminf(mn, smn[k]), mx = fmaxf(mx, smx[k]);
-        mn = fminf(mn, smn[0]), mx = fmaxf(mx, smx[0]);
+        for (int k = 0; k < kExtThreads / 32; ++k) mn = fminf(mn, smn[k]), mx = fmaxf(mx, smx[k]);
         // centre rows floor(lr + flow_y) for lr in [lr0, lr1): 3x3 taps around them, one more row of slack; the rows
         // [lr0, lr1) themselves are read for the robustness
         const float flo = fmaxf((float)lr0 + mn - 3.0f, 0.0f), fhi = fminf((float)lr1 + mx + 3.0f, (float)H);
@@ -61,9 +73,20 @@ __global__ void __launch_bounds__(256) band_copy_kernel(const __grid_constant__ 
     const size_t begin = (size_t)(plane == 2 ? e.z : e.x) * row, end = (size_t)(plane == 2 ? e.w : e.y) * row;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if ((row & 3) == 0) {
+        // 4 x 16 bytes in flight per thread (the loads of one iteration are independent): NVLink latency is several
+        // microseconds under load and one outstanding load per thread leaves the links half idle
         const float4 *s4 = reinterpret_cast<const float4 *>(src);
         float4 *d4 = reinterpret_cast<float4 *>(dst);
-        for (size_t i = begin / 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end / 4; i += stride) d4[i] = s4[i];
+        const size_t e4 = end / 4;
+        for (size_t i0 = begin / 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < e4; i0 += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * stride < e4) v[u] = s4[i0 + u * stride];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * stride < e4) d4[i0 + u * stride] = v[u];
+        }
     } else {
         for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) dst[i] = src[i];
     }
@@ -95,7 +118,7 @@ extern "C" int hhsr_gather_bands(const float *const *raws, const float *const *r
         l.raw_l[f] = raws_local[f], l.r_l[f] = rs_local[f], l.covs_l[f] = has_covs ? covs_local[f] : nullptr, l.flow_l[f] = flows_local[f];
     }
     cudaStream_t st = (cudaStream_t)stream;
-    band_extents_kernel<<<n_frames, 256, 0, st>>>(l, ny, nx, ts, H, lr_begin, lr_end, reinterpret_cast<int4 *>(extents));
+    band_extents_kernel<<<n_frames, kExtThreads, 0, st>>>(l, ny, nx, ts, H, lr_begin, lr_end, reinterpret_cast<int4 *>(extents));
     band_copy_kernel<<<dim3(148, 3, n_frames), 256, 0, st>>>(l, W, reinterpret_cast<const int4 *>(extents));
     return launch_status("gather_bands");
 }

@@ -45,6 +45,8 @@ SIGNATURES = {
     "hhsr_merge_ref": [_P, _I, _I, _P, _P, _P, _I, _I, _D, _IP, _I, _P, _I, _I, _D, _I, _I, _I, _P],
     "hhsr_merge_accumulate_rows": [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _I,
                                    _I, _P, _P, _I, _I, _D, _IP, _I, _I, _I, _I, _P],
+    "hhsr_merge_finish_rows": [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _I,
+                               _I, _P, _P, _I, _I, _D, _IP, _I, _I, _I, _I, _P, _P, _P, _P],
     "hhsr_merge_ref_rows": [_P, _I, _I, _P, _P, _P, _I, _I, _D, _IP, _I, _P, _I, _I, _D, _I, _I, _I, _P],
     "hhsr_gather_bands": [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                           C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],

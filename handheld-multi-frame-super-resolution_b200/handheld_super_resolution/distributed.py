@@ -220,7 +220,9 @@ class RowShardedMerge:
         r0, r1 = self.row_slice
         rows = r1 - r0
         out = torch.empty((rows, self.Ws, 3), dtype=torch.float32, device=self.num.device) if rows > 0 else None
+        from .super_resolution import _mark
         self.hdl.barrier(channel=0)                 # every rank has published its frames: THE exchange point
+        _mark("rows_barrier")
         try:
             if rows > 0 and n > 0:
                 F = self.slot_floats * 4
@@ -235,10 +237,18 @@ class RowShardedMerge:
                           arr([p + 3 * P for p in src]), arr(dst), arr([p + P for p in dst]),
                           arr([0 if iso else p + 2 * P for p in dst]), arr([p + 3 * P for p in dst]), n, self.H, self.W,
                           self.ny, self.nx, int(self.ts), lr0, lr1, _lib.ptr(self.extents), _lib.stream())
-                _lib.call("hhsr_merge_accumulate_rows", arr(dst), arr([p + 3 * P for p in dst]),
-                          arr([0 if iso else p + 2 * P for p in dst]), arr([p + P for p in dst]), n, self.H, self.W, self.ny,
-                          self.nx, int(self.ts), _lib.ptr(self.num), _lib.ptr(self.den), self.Hs, self.Ws, float(self.scale),
-                          _lib.cfa_array(cfa_pattern), int(iso), 1, r0, r1, _lib.stream())
+                _mark("rows_gather")
+                from .merge import fast_path_applies
+                fused = not config.accumulated_robustness_denoiser.enabled and fast_path_applies(self.H, self.W, self.scale, self.ts)
+                margs = (arr(dst), arr([p + 3 * P for p in dst]), arr([0 if iso else p + 2 * P for p in dst]),
+                         arr([p + P for p in dst]), n, self.H, self.W, self.ny, self.nx, int(self.ts), _lib.ptr(self.num),
+                         _lib.ptr(self.den), self.Hs, self.Ws, float(self.scale), _lib.cfa_array(cfa_pattern), int(iso), 1, r0, r1)
+                if fused:      # all frames + the reference frame + divide in ONE pass: only the finished slice is written
+                    _lib.call("hhsr_merge_finish_rows", *margs, _lib.ptr(ref_img), _lib.ptr(None if iso else covs_ref),
+                              _lib.ptr(out), _lib.stream())
+                else:
+                    _lib.call("hhsr_merge_accumulate_rows", *margs, _lib.stream())
+                _mark("rows_merge")
                 if acc_rob is not None:
                     # accumulated robustness of the LR rows [lr0, lr1) this slice looks at (merge_ref reads it at
                     # rint(oy / scale)): the sum over ALL frames in burst order, from the gathered bands; the other rows
@@ -251,7 +261,8 @@ class RowShardedMerge:
                     add_many(acc_rob[lr0:lr1], [r_rows(f) for f in range(n)])
             elif rows > 0:
                 self.num.zero_(), self.den.zero_()
-            if rows > 0:
+                fused = False
+            if rows > 0 and not fused:
                 ard = config.accumulated_robustness_denoiser
                 if ard.enabled:
                     acc, rad_max, max_mult, max_fc = acc_rob, int(ard.merge.rad_max), float(ard.merge.max_multiplier), int(ard.merge.max_frame_count)
@@ -261,9 +272,27 @@ class RowShardedMerge:
                           _lib.ptr(self.num), _lib.ptr(self.den), self.Hs, self.Ws, float(self.scale), _lib.cfa_array(cfa_pattern),
                           int(iso), _lib.ptr(acc), max_fc, rad_max, max_mult, 1, r0, r1, _lib.stream())
                 out.copy_(self.num)
+            _mark("rows_merge_ref")
         finally:
             self.hdl.barrier(channel=1)             # all bands pulled: the owners may overwrite their slots (next burst)
         return out
+
+
+def broadcast_reference_frame(ref_img, group=None):
+    """Every rank needs the reference frame.  When it lives in host memory, rank 0 uploads it once and NCCL broadcasts it
+    over NVLink (48 MB at 12 MP) instead of every rank pulling its own copy through the host's PCIe complex — with 8
+    ranks that is 7 frames less of host-to-device traffic per burst.  Input distribution only: the merge path still has
+    its single exchange point.  Device-resident frames pass through."""
+    if isinstance(ref_img, torch.Tensor) and ref_img.is_cuda:
+        return ref_img
+    from .super_resolution import _host_tensor
+    host = _host_tensor(ref_img)
+    buf = torch.empty(host.shape, dtype=host.dtype, device=torch.device("cuda", torch.cuda.current_device()))
+    if dist.get_rank(group) == 0:
+        buf.copy_(host, non_blocking=True)
+    wire = buf.view(torch.int16) if buf.dtype == torch.uint16 else buf
+    dist.broadcast(wire, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return buf
 
 
 def main_sharded(ref_img, comp_imgs, config, group=None, mode=None):
@@ -282,19 +311,24 @@ def main_sharded(ref_img, comp_imgs, config, group=None, mode=None):
         rank, world = 0, 1
     mode = mode or os.environ.get("HHSR_SHARD_REDUCE", "reduce_scatter")
     ids = shard_frames(len(comp_imgs), rank, world)
+    ahead = None
+    if world > 1:
+        ref_img = broadcast_reference_frame(ref_img, group)
+        ahead = max(1, min(len(ids), int(os.environ.get("HHSR_SHARD_ALIGN_AHEAD", "3"))))   # few frames per rank: run their chains together
     if mode == "rows" and world > 1:
         H, W = ref_img.shape
         rs = RowShardedMerge.get(H, W, config.scale, len(comp_imgs), int(config.block_matching.tuning.tile_size), group)
-        out, dbg = main(ref_img, comp_imgs, config, frame_ids=ids, frame_sink=rs, finalize_fn=rs.finalize)
+        out, dbg = main(ref_img, comp_imgs, config, frame_ids=ids, frame_sink=rs, finalize_fn=rs.finalize, align_ahead=ahead)
         dbg["rows"] = rs.row_slice
         return out, dbg
     if mode == "p2p" and world > 1:
         H, W = ref_img.shape
         s = config.scale
         red = P2PReduce.get((round(s * H), round(s * W), 3), group)
-        return main(ref_img, comp_imgs, config, frame_ids=ids, accumulators=(red.num, red.den), finalize_fn=red.finalize)
+        return main(ref_img, comp_imgs, config, frame_ids=ids, accumulators=(red.num, red.den), finalize_fn=red.finalize,
+                    align_ahead=ahead)
     if mode == "allreduce":
         fn = lambda n, d, a: allreduce_accumulators(n, d, a, group)   # noqa: E731
     else:
         fn = lambda n, d, a: reduce_scatter_accumulators(n, d, a, group)   # noqa: E731
-    return main(ref_img, comp_imgs, config, frame_ids=ids, reduce_fn=fn)
+    return main(ref_img, comp_imgs, config, frame_ids=ids, reduce_fn=fn, align_ahead=ahead)

@@ -33,11 +33,21 @@ def merge(comp_img, alignments, covs, r, num, den, cfa_pattern, config, init=Fal
 MERGE_INIT, MERGE_GENERIC = 1, 2      # include/hhsr.h: HHSR_MERGE_INIT, HHSR_MERGE_GENERIC
 
 
-def merge_batch(comp_imgs, alignments, covs, rs, num, den, cfa_pattern, config, init=False, generic=False):
+def fast_path_applies(H, W, scale, tile_size):
+    """Whether the power-of-two merge kernels run (scales 1, 2, 4; output width a multiple of 4; power-of-two tile size
+    >= 4) — the condition of csrc/merge.cu pow2_fast_shift(), needed on the host to plan the fused finish."""
+    ts = int(tile_size)
+    return scale in (1, 2, 4) and (W * int(scale)) % 4 == 0 and ts >= 4 and ts & (ts - 1) == 0
+
+
+def merge_batch(comp_imgs, alignments, covs, rs, num, den, cfa_pattern, config, init=False, generic=False, finish=None):
     """Same arithmetic as calling merge() once per frame in list order (bit-identical), in ONE pass over num/den: the
     accumulators are read and written once instead of once per frame (B200 addition, SURVEY section 8d "K-frame
     batched merge").  init=True: the batch initialises num/den (their previous contents are ignored) — what main() does
-    with the first batch of a burst.  generic=True forces the any-scale kernel (A/B parity tests)."""
+    with the first batch of a burst.  generic=True forces the any-scale kernel (A/B parity tests).
+    finish=(ref_img, ref_kernels): this is the LAST batch of the burst — merge_ref (plain mode) and utils.divide follow in
+    the same pass on the register accumulators and `num` receives the finished image (bit-identical to merge_batch +
+    merge_ref(fuse_divide=True)); `den` is left untouched.  Needs fast_path_applies()."""
     if config.mode != "bayer":
         raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
     _check_acc(num, den)
@@ -46,6 +56,13 @@ def merge_batch(comp_imgs, alignments, covs, rs, num, den, cfa_pattern, config, 
     iso = config.merging.kernel == "iso"
     ny, nx, _ = alignments[0].shape
     arr = lambda ts: (C.c_void_p * K)(*[t.data_ptr() if t is not None else 0 for t in ts])  # noqa: E731
+    if finish is not None:
+        ref_img, ref_kernels = finish
+        _lib.call("hhsr_merge_finish_rows", arr(comp_imgs), arr(alignments), arr([None] * K if iso else covs), arr(rs),
+                  K, H, W, ny, nx, int(config.block_matching.tuning.tile_size), _lib.ptr(num), _lib.ptr(den), num.shape[0],
+                  num.shape[1], float(config.scale), _lib.cfa_array(cfa_pattern), int(iso), MERGE_INIT if init else 0,
+                  0, num.shape[0], _lib.ptr(ref_img), _lib.ptr(None if iso else ref_kernels), _lib.ptr(num), _lib.stream())
+        return
     _lib.call("hhsr_merge_accumulate_batch", arr(comp_imgs), arr(alignments), arr([None] * K if iso else covs), arr(rs),
               K, H, W, ny, nx, int(config.block_matching.tuning.tile_size), _lib.ptr(num), _lib.ptr(den), num.shape[0],
               num.shape[1], float(config.scale), _lib.cfa_array(cfa_pattern), int(iso),

@@ -8,7 +8,7 @@ import torch
 
 from .alignment import align, init_alignment
 from .kernels import estimate_kernels
-from .merge import merge, merge_batch, merge_ref
+from .merge import fast_path_applies, merge, merge_batch, merge_ref
 from .params import sanitize_config, update_snr_config
 from .robustness import compute_robustness, init_robustness
 from .utils import add_many, timer
@@ -55,6 +55,9 @@ ALIGN_AHEAD = int(os.environ.get("HHSR_ALIGN_AHEAD", "1"))   # alignment chains 
 # accumulator traffic — and 5 frames per pass when they stream in from the host, so that merging overlaps the uploads
 # and only the last short batch is left when the last frame arrives.
 MERGE_BATCH = int(os.environ.get("HHSR_MERGE_BATCH", "0"))
+# the last batch of a burst also merges the reference frame and divides (merge.merge_batch(finish=...)): num / den never
+# return to HBM.  False keeps merge_ref + divide as a separate pass (the reference's structure; tests compare the two).
+FUSE_FINISH = True
 
 
 def _host_tensor(frame):
@@ -154,7 +157,7 @@ class FrameFeeder:
 
 
 def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulators=None, finalize_fn=None, merge_batch_size=None,
-         frame_sink=None):
+         frame_sink=None, align_ahead=None):
     """Device pipeline (super_resolution.py:41-200).
 
     ref_img [H,W], comp_imgs [N-1,H,W]: float32 host arrays (numpy / pinned torch) or CUDA tensors.
@@ -169,7 +172,8 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     is bit-identical for every batch size).  `frame_sink` (with finalize_fn): an object with `outputs(k) -> (r, covs)`
     (buffers the k-th frame's robustness and covariances are written into) and `publish(k, im_id, frame, flow, covs, r)`:
     the aligned frames are handed over instead of being merged here and no accumulators are allocated — the row-sharded
-    multi-GPU merge (distributed.RowShardedMerge) merges all frames of all ranks into this rank's slice of output rows."""
+    multi-GPU merge (distributed.RowShardedMerge) merges all frames of all ranks into this rank's slice of output rows.
+    `align_ahead`: alignment chains in flight on side streams (default ALIGN_AHEAD = 1)."""
     verbose_2 = config.verbose >= 2
     grey_method = config.grey_method
     if config.mode != "bayer":
@@ -235,8 +239,15 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     feed = FrameFeeder(comp_imgs, ids, config, dev, extra_slots=batch_size - 1)
     pending = []        # (k, frame, flow, covs, r) of the frames waiting for the next pass over the accumulators
     merged_any = False
+    # the last batch can absorb merge_ref + divide (one pass less over num / den): plain single-GPU runs on the fast path
+    fuse_finish = (FUSE_FINISH and frame_sink is None and finalize_fn is None and reduce_fn is None and len(ids) > 0
+                   and not config.accumulated_robustness_denoiser.enabled
+                   and fast_path_applies(H, W, scale, config.block_matching.tuning.tile_size))
+    covs_ref = estimate_kernels_(cuda_ref_img, config) if fuse_finish else None
     main_stream = torch.cuda.current_stream(dev)
-    ahead = 0 if (os.environ.get("HHSR_SINGLE_STREAM", "0") == "1" or verbose_2) else ALIGN_AHEAD
+    # alignment chains in flight ahead of the merge, each on its own side stream.  One is enough to keep a single GPU busy
+    # (more measure the same); a rank of a multi-GPU run has 2-3 frames and latency-bound chains, so it runs them all at once
+    ahead = 0 if (os.environ.get("HHSR_SINGLE_STREAM", "0") == "1" or verbose_2) else (ALIGN_AHEAD if align_ahead is None else int(align_ahead))
 
     def start_alignment(k):
         """Frame k: H2D wait (+ uint16 normalisation) on the main stream, then grey image and alignment on one of the
@@ -281,7 +292,11 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
         pending.append((k, cuda_img, flow, covs, r))
         if len(pending) == batch_size or k == len(ids) - 1:
             # one pass over num/den for the whole batch; the first batch of a burst initialises them
-            if len(pending) == 1:
+            if fuse_finish and k == len(ids) - 1:
+                merge_batch_([p[1] for p in pending], [p[2] for p in pending], [p[3] for p in pending],
+                             [p[4] for p in pending], num, den, cfa_pattern, config, init=not merged_any,
+                             finish=(cuda_ref_img, covs_ref))
+            elif len(pending) == 1:
                 merge_(cuda_img, flow, covs, r, num, den, cfa_pattern, config, init=not merged_any)
             else:
                 merge_batch_([p[1] for p in pending], [p[2] for p in pending], [p[3] for p in pending],
@@ -312,9 +327,10 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
             rows, gather_fn = res
     _mark("reduce")
 
-    covs = estimate_kernels_(cuda_ref_img, config)
-    use_acc = accumulated_r if config.accumulated_robustness_denoiser.enabled else None
-    merge_ref_(cuda_ref_img, covs, num, den, cfa_pattern, config, use_acc, fuse_divide=True, rows=rows)   # + utils.divide, :191
+    if not fuse_finish:
+        covs = estimate_kernels_(cuda_ref_img, config)
+        use_acc = accumulated_r if config.accumulated_robustness_denoiser.enabled else None
+        merge_ref_(cuda_ref_img, covs, num, den, cfa_pattern, config, use_acc, fuse_divide=True, rows=rows)   # + utils.divide, :191
     _mark("merge_ref")
     if gather_fn is not None:
         gather_fn(num)

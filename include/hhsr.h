@@ -186,6 +186,18 @@ int hhsr_merge_accumulate_rows(const float *const *raws, const float *const *flo
                                const float *const *rs, int K, int H, int W, int ny, int nx, int ts, float *num_rows,
                                float *den_rows, int Hs, int Ws, double scale, const int *cfa_host, int iso, int flags,
                                int row_begin, int row_end, hhsr_stream_t stream);
+/* The LAST batch of a burst fused with merge_ref and divide (B200 addition): as hhsr_merge_accumulate_rows, then — in
+ * the same pass, on the register accumulators — the reference frame's window sums (merge.py:82-233, plain mode: no
+ * accumulated-robustness denoiser) and the quotient num / den (utils.py:62-90); only the finished image rows are
+ * written to out_rows (pointing at row `row_begin`), num_rows / den_rows are read (unless HHSR_MERGE_INIT) but NOT
+ * written.  Bit-identical to hhsr_merge_accumulate_rows + hhsr_merge_ref_rows(fuse_divide); 48 B per HR pixel less HBM
+ * traffic and one launch less.  Needs the power-of-two fast path (scale 1, 2 or 4, Ws % 4 == 0): HHSR_E_UNSUPPORTED
+ * otherwise.  With HHSR_MERGE_INIT num_rows / den_rows are only used as scratch when K > 24. */
+int hhsr_merge_finish_rows(const float *const *raws, const float *const *flows, const float *const *covs,
+                           const float *const *rs, int K, int H, int W, int ny, int nx, int ts, float *num_rows,
+                           float *den_rows, int Hs, int Ws, double scale, const int *cfa_host, int iso, int flags,
+                           int row_begin, int row_end, const float *ref_raw, const float *ref_covs, float *out_rows,
+                           hhsr_stream_t stream);
 /* hhsr_merge_ref on slice buffers: num_rows / den_rows point at row `row_begin`. */
 int hhsr_merge_ref_rows(const float *raw, int H, int W, const float *covs, float *num_rows, float *den_rows, int Hs, int Ws,
                         double scale, const int *cfa_host, int iso, const double *acc_rob, int max_frame_count, int rad_max,

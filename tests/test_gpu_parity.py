@@ -444,6 +444,8 @@ def test_merge_pow2_fast_path_equals_generic(scale, cfa):
         for init in (False, True):
             seq_n = torch.rand((scale * H, scale * W, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
             seq_d = seq_n.clone() + 1.0
+            seq_n0, seq_d0 = seq_n.clone(), seq_d.clone()
+            raw2 = raw.flip(0).contiguous()          # stands in for the reference frame
             bat_n, bat_d = seq_n.clone(), seq_d.clone()
             gen_n, gen_d = seq_n.clone(), seq_d.clone()
             for k in range(3):
@@ -452,6 +454,12 @@ def test_merge_pow2_fast_path_equals_generic(scale, cfa):
             MG.merge_batch([raw] * 3, flows, [covs] * 3, rs, gen_n, gen_d, cfa, cfg, init=init, generic=True)
             assert torch.equal(seq_n, bat_n) and torch.equal(seq_d, bat_d), (scale, cfa, kern, init, "batched fast path")
             assert torch.equal(seq_n, gen_n) and torch.equal(seq_d, gen_d), (scale, cfa, kern, init, "batched generic")
+            # last batch fused with merge_ref + divide: only the image is written, bit-identical to the separate passes
+            if True:
+                fin_n, fin_d = (torch.full_like(seq_n, float("nan")), torch.full_like(seq_d, 3.0)) if init else (seq_n0.clone(), seq_d0.clone())
+                MG.merge_ref(raw2, covs, seq_n, seq_d, cfa, cfg, fuse_divide=True)
+                MG.merge_batch([raw] * 3, flows, [covs] * 3, rs, fin_n, fin_d, cfa, cfg, init=init, finish=(raw2, covs))
+                assert torch.equal(torch.nan_to_num(seq_n, nan=-7.0), torch.nan_to_num(fin_n, nan=-7.0)), (scale, cfa, kern, init, "fused finish")
 
 
 @pytest.mark.parametrize("shape", [(64, 96), (70, 100), (37, 53), (5, 8), (3000, 4000)])
@@ -726,9 +734,12 @@ def test_properties_full_size():
 # ------------------------------------------------------------------------------------------------ noise curves
 def test_noise_curves_gpu_monte_carlo():
     """hhsr_noise_mc (seeded Philox Monte-Carlo, one CTA per brightness level) behind noise_model.run_fast_MC, against
-    the reference's own curves data/noise_model_{std,diff}_ISO_100.npy.  Those are themselves Monte-Carlo estimates
-    from 1e5 patch pairs (relative standard error ~0.05 % on sigma, ~0.24 % on d per level, carried into the
-    interpolated middle of the curves), so the comparison is statistical: 5 standard errors of the reference."""
+    the reference's own curves data/noise_model_{std,diff}_ISO_100.npy.  Those files are themselves Monte-Carlo
+    estimates and visibly noisy level by level (neighbouring levels of the stored d curve scatter by ~1 %, also in the
+    middle of the range, where run_fast_MC would give a smooth interpolation: they were not produced by today's
+    run_fast_MC); a 4e5-patch NumPy run of the reference's estimator differs from them by the same 1.6 % / 2.4 % maxima
+    at the same levels (19 and 26) as the device kernel.  So: loose bounds against the files, tight bounds (5 standard
+    errors) against the NumPy estimator and against the closed form."""
     from handheld_super_resolution.noise_model import regular_MC, regular_MC_numpy, run_fast_MC
     alpha, beta = 1.80710882e-4, 3.1937599182128e-6
     s1, d1 = run_fast_MC(alpha, beta, seed=0, n_patches=400000)
@@ -740,7 +751,7 @@ def test_noise_curves_gpu_monte_carlo():
     es, ed = np.abs(s1 - std) / std, np.abs(d1 - diff) / diff
     record("noise_curves_rel_err_vs_reference", {"sigma_max": float(es.max()), "d_max": float(ed.max()),
                                                  "sigma_mean": float(es.mean()), "d_mean": float(ed.mean())})
-    assert es.max() < 0.004 and ed.max() < 0.015
+    assert es.max() < 0.025 and es.mean() < 0.004 and ed.max() < 0.04 and ed.mean() < 0.01
     # the estimator itself, level by level, against NumPy on clipped and unclipped brightness levels (independent random
     # numbers: 5 standard errors of the two estimates)
     b = np.array([0.0, 0.001, 0.003, 0.01, 0.2, 0.7, 0.995, 0.999, 1.0])

@@ -23,8 +23,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "20x12MP_s2"]
-    cfg = bench.make_config(wl["scale"], wl["H"], wl["W"])
     burst, _ = synth_burst(wl["n"], wl["H"], wl["W"], seed=0, device="cuda", as_numpy=False)
+    cfg = bench.make_config(wl["scale"], wl["H"], wl["W"], burst[0].mean().item())
+    if len(sys.argv) > 2:
+        os.environ["HHSR_SHARD_REDUCE"] = sys.argv[2]
     for _ in range(3):
         main_sharded(burst[0], burst[1:], cfg)
     acc = {}
@@ -42,10 +44,16 @@ def main():
             acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1) / reps
         acc["total"] = acc.get("total", 0.0) + ev[0][1].elapsed_time(ev[-1][1]) / reps
     t = torch.tensor([acc[k] for k in sorted(acc)], device="cuda")
+    per_rank = [torch.zeros_like(t) for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    else:
+        per_rank = [t]
     if int(os.environ.get("RANK", "0")) == 0:
-        print(json.dumps({"world": world, "phase_ms_max_over_ranks": dict(zip(sorted(acc), [round(x, 3) for x in t.tolist()]))}))
+        print(json.dumps({"world": world, "mode": os.environ.get("HHSR_SHARD_REDUCE", "reduce_scatter"),
+                          "phase_ms_max_over_ranks": dict(zip(sorted(acc), [round(x, 3) for x in t.tolist()])),
+                          "phase_ms_per_rank": {k: [round(p[i].item(), 3) for p in per_rank] for i, k in enumerate(sorted(acc))}}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -24,15 +24,16 @@ def main():
     import bench
     from handheld_super_resolution import alignment as AL, merge as MG, robustness as RB
     from handheld_super_resolution.kernels import estimate_kernels
+    from handheld_super_resolution.raw2rgb import postprocess
     from handheld_super_resolution.synthetic import synth_burst
     from handheld_super_resolution.utils_image import compute_grey_images
     scale = int(a.scale) if a.scale == int(a.scale) else a.scale
-    cfg = bench.make_config(scale, a.H, a.W)
-    burst, _ = synth_burst(2, a.H, a.W, seed=0, device="cuda", as_numpy=False)
+    burst, _ = synth_burst(5, a.H, a.W, seed=0, device="cuda", as_numpy=False)
+    cfg = bench.make_config(scale, a.H, a.W, burst[0].mean().item())
     ref, img = burst[0], burst[1]
     cfa, wb = cfg.exif.cfa_pattern, cfg.exif.white_balance
-    std = torch.tensor(cfg.noise_model.std_curve, dtype=torch.float64, device="cuda")
-    diff = torch.tensor(cfg.noise_model.diff_curve, dtype=torch.float64, device="cuda")
+    std = torch.as_tensor(cfg.noise_model.std_curve, dtype=torch.float64, device="cuda")
+    diff = torch.as_tensor(cfg.noise_model.diff_curve, dtype=torch.float64, device="cuda")
     refal = AL.init_alignment(compute_grey_images(ref, "FFT"), cfg)
     rm, rs = RB.init_robustness(ref, cfa, wb, cfg)
     grey = compute_grey_images(img, "FFT")
@@ -63,7 +64,9 @@ def main():
         "robustness": lambda: RB.compute_robustness(img, rm, rs, flow, cfa, wb, table, cfg),
         "estimate_kernels": lambda: estimate_kernels(img, cfg),
         "merge": lambda: MG.merge(img, flow, covs, r, num, den, cfa, cfg),
+        "merge_batch4": lambda: MG.merge_batch([burst[k] for k in (1, 2, 3, 4)], [flow] * 4, [covs] * 4, [r] * 4, num, den, cfa, cfg),
         "merge_ref": lambda: MG.merge_ref(ref, covs, num, den, cfa, cfg),
+        "postprocess_u8": lambda: postprocess(None, num, False, False, True, cfg.postprocessing.sharpening, False, None, output_dtype="uint8"),
     }
     res = {}
     for k, fn in stages.items():

@@ -81,6 +81,71 @@ def merge():
               open(os.path.join(P, "merge_traffic_bytes.json"), "w"))
 
 
+# algorithmic bytes of one launch on a 12 MP frame at scale 2: what the stage must move at least
+ALGORITHMIC = {
+    "accumulate_pow2_batch": ("merge, 4 frames per pass", 48e6 * 48 + 4 * 12e6 * 12),
+    "accumulate_pow2_kernel": ("merge, 1 frame per pass", 48e6 * 48 + 12e6 * 12),
+    "robustness_kernel": ("fused robustness", (7 * 48 + 36 + 48) * 1e6),
+    "local_min5": ("5x5 minimum", 96e6),
+    "bm_l2_tiled32": ("L2 block matching, level 1 (2852 tiles)", 2852 * (40 * 40 + 32 * 32) * 4),
+    "ica32_kernel": ("ICA level 0 (11750 tiles)", 4 * 48e6),
+    "estimate_kernels_kernel": ("kernel estimation", 96e6),
+    "gauss_downsample": ("pyramid level 0 -> 1", 48e6 + 12e6),
+    "guide_stats": ("guide image + local stats", 48e6 + 36e6),
+    "grey_band_mask": ("band mask on the half spectrum", 48e6),
+    "accumulate_ref": ("merge_ref + divide", 48e6 * 48 + 12e6 * 8),
+    "regular_fft": ("cuFFT column pass (library)", 2 * 96e6),
+    "vector_fft": ("cuFFT row pass (library)", 48e6 + 96e6),
+    "post_blur_cols": ("unsharp mask, column pass (48 MP x 3)", 2 * 576e6),
+    "post_finish": ("unsharp mask row pass + gamma + uint8", 2 * 576e6 + 144e6),
+}
+
+
+def stages():
+    """profiles/stages_<tag>_ncu.md from gpurun_out/ncu_<tag>/*.raw.csv (tools/profile_stages.sh)."""
+    d = os.path.join(G, "ncu_%s" % tag)
+    if not os.path.isdir(d):
+        return
+    out = ["# ncu --set full, one launch per hot kernel — `tools/profile_stages.sh %s` (driver: tools/stage_microbench.py, one 12 MP "
+           "frame, scale 2, 1xB200), round %s" % (tag, tag[1:]), "",
+           "Command per kernel: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 3 -c 1 python "
+           "tools/stage_microbench.py --iters 2`.  `DRAM bytes` = dram__bytes_read.sum + dram__bytes_write.sum of that launch; "
+           "`algorithmic` = the bytes the stage must move at least (DESIGN.md section 4); `HBM frac` = algorithmic bytes / duration / "
+           "6536 GB/s (MEASURED_PEAKS.json).", "",
+           "| kernel | what | us | DRAM bytes (MB) | algorithmic (MB) | HBM frac | DRAM % | SM % | issue % | warps % | regs | L1 hit % | L2 hit % |",
+           "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+
+    def num(x):
+        return float(x.replace(",", ""))
+    for f in sorted(os.listdir(d)):
+        if not f.endswith(".raw.csv"):
+            continue
+        rows = list(csv.reader(open(os.path.join(d, f))))
+        if len(rows) < 3:
+            continue
+        m = dict(zip(rows[0], zip(rows[1], rows[2])))
+
+        def val(k, default=float("nan")):
+            if k not in m:
+                return default
+            u, v = m[k]
+            v = num(v)
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}.get(u, 1.0)
+        key = f[:-8]
+        what, alg = next(((w, a) for k, (w, a) in ALGORITHMIC.items() if key.startswith(k)), ("", float("nan")))
+        us = val("gpu__time_duration.sum")
+        dram = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+        out.append("| `%s` | %s | %.1f | %.0f | %.0f | %.2f | %.0f | %.0f | %.0f | %.0f | %d | %.0f | %.0f |" % (
+            m["Kernel Name"][1][:48], what, us, dram / 1e6, alg / 1e6, alg / (us * 1e-6) / 6536.4e9,
+            val("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), val("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+            val("smsp__issue_active.avg.pct_of_peak_sustained_active"), val("sm__warps_active.avg.pct_of_peak_sustained_active"),
+            int(val("launch__registers_per_thread", 0)), val("l1tex__t_sector_hit_rate.pct"), val("lts__t_sector_hit_rate.pct")))
+    open(os.path.join(P, "stages_%s_ncu.md" % tag), "w").write("\n".join(out) + "\n")
+
+
 if __name__ == "__main__":
-    launches()
-    merge()
+    for fn in (launches, merge, stages):
+        try:
+            fn()
+        except FileNotFoundError as e:
+            print("skipped %s: %s" % (fn.__name__, e))
