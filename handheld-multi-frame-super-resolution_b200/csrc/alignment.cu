@@ -176,19 +176,18 @@ __global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ re
 // preserved.  A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: while it searches one tile, the window and the
 // reference pixels of its next tile are already in flight (registers), so the global-memory latency that bounded the
 // one-tile-per-CTA version (long-scoreboard stalls, FP64 pipe 40 % busy) is off the critical path.
+constexpr int BM_RW = 8, BM_NW = 32 / BM_RW, BM_NT = 32 * BM_NW;     // tile rows per warp, warps and threads per CTA
 template <int R>
-__global__ void __launch_bounds__(256, 2) bm_l2_tiled32_kernel(const float *__restrict__ ref, int ref_w, const float *__restrict__ mov,
-                                                               int mov_h, int mov_w, float2 *__restrict__ flow, int nx, int ntiles) {
-    constexpr int TS = 32, N = 2 * R + 1, SW = TS + 2 * R, RW = 4, UG = 3, NG = (N + UG - 1) / UG, NV = N * UG;
-    constexpr int NWIN = SW * SW, PF = (NWIN + 255) / 256;
+__global__ void __launch_bounds__(BM_NT, 3) bm_l2_tiled32_kernel(const float *__restrict__ ref, int ref_w, const float *__restrict__ mov,
+                                                                 int mov_h, int mov_w, float2 *__restrict__ flow, int nx, int ntiles) {
+    constexpr int TS = 32, N = 2 * R + 1, SW = TS + 2 * R, RW = BM_RW, NW = BM_NW, NT = BM_NT, UG = 3, NG = (N + UG - 1) / UG, NV = N * UG;
+    constexpr int NWIN = SW * SW, PF = (NWIN + NT - 1) / NT, VG = (N + 2) / 3;
     static_assert(NV <= 32, "search radius too large for the tiled kernel");
     extern __shared__ double bsm[];
     double *s_win0 = bsm;                       // [2][SW][SW]
-    double *s_red = s_win0 + 2 * NWIN;          // [8][NV][33]
-    double *s_part = s_red + 8 * NV * 33;       // [8][N*N]
-    double *s_col = s_part + 8 * N * N;         // [N][SW]
-    double *s_S = s_col + N * SW;               // [N*N]
-    double *s_err = s_S + N * N;                // [N*N]
+    double *s_part = s_win0 + 2 * NWIN;         // [NW][N*N]
+    double *s_col = s_part + NW * N * N;        // [N][SW]
+    double *s_err = s_col + N * SW;             // [N*N]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int yb = warp * RW;
 
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(256, 2) bm_l2_tiled32_kernel(const float *__re
     if (t < ntiles) {
         f = flow[t];
         const int fx = (int)rintf(f.x), fy = (int)rintf(f.y);                    // flow.round(), :352
-        for (int i = tid; i < NWIN; i += 256) s_win0[i] = (double)win_load(t, fx, fy, i);
+        for (int i = tid; i < NWIN; i += NT) s_win0[i] = (double)win_load(t, fx, fy, i);
 #pragma unroll
         for (int k = 0; k < RW; ++k) rfn[k] = ref_load(t, k);
     }
@@ -229,23 +228,31 @@ __global__ void __launch_bounds__(256, 2) bm_l2_tiled32_kernel(const float *__re
             const int fx = (int)rintf(fn.x), fy = (int)rintf(fn.y);
 #pragma unroll
             for (int q = 0; q < PF; ++q) {
-                const int i = tid + q * 256;
+                const int i = tid + q * NT;
                 pf[q] = (i < NWIN) ? win_load(tn, fx, fy, i) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < RW; ++k) rfn[k] = ref_load(tn, k);
         }
-        // S, step 1: column sums of m^2 for every vertical shift
-        for (int c = tid; c < N * SW; c += 256) {
-            const int v = c / SW, X = c - v * SW;
-            const double *q = s_win + v * SW + X;
-            double a = 0.0;
-#pragma unroll 8
-            for (int y = 0; y < TS; ++y) a = fma(q[y * SW], q[y * SW], a);
-            s_col[c] = a;
+        // S, step 1: column sums of m^2 for every vertical shift.  Task = (column X, group of 3 shifts): the TS + 2 rows it
+        // needs are read once and feed up to 3 sums, each accumulated over its 32 rows in ascending order
+        for (int c = tid; c < VG * SW; c += NT) {
+            const int vg = c / SW, X = c - vg * SW, v0 = vg * 3;
+            const double *q = s_win + v0 * SW + X;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 2
+            for (int y = 0; y < TS + 2; ++y) {
+                const double m = (v0 * SW + X + y * SW < NWIN) ? q[y * SW] : 0.0;
+                const double mm = __dmul_rn(m, m);      // explicit roundings: the three sums must round alike (equal windows)
+                if (y < TS) a0 = __dadd_rn(a0, mm);
+                if (y >= 1 && y < TS + 1) a1 = __dadd_rn(a1, mm);
+                if (y >= 2) a2 = __dadd_rn(a2, mm);
+            }
+            s_col[v0 * SW + X] = a0;
+            if (v0 + 1 < N) s_col[(v0 + 1) * SW + X] = a1;
+            if (v0 + 2 < N) s_col[(v0 + 2) * SW + X] = a2;
         }
         // C: register-tiled cross term
-        double *red = s_red + warp * (NV * 33);
         for (int g = 0; g < NG; ++g) {
             double acc[N][UG];
 #pragma unroll
@@ -269,22 +276,25 @@ __global__ void __launch_bounds__(256, 2) bm_l2_tiled32_kernel(const float *__re
                     }
                 }
             }
+            // sum over the 32 lanes without shared memory: transpose-reduction by butterflies (16 + 8 + 4 + 2 + 1 exchanges);
+            // accumulator i ends in lane i.  Every accumulator goes through the same pairing tree (lane l with l^16, then
+            // ^8, ...), and IEEE addition commutes, so equal windows still give bit-equal totals
+            double a[32];
 #pragma unroll
-            for (int v = 0; v < N; ++v)
+            for (int i = 0; i < 32; ++i) a[i] = (i < NV) ? acc[i / UG][i % UG] : 0.0;
 #pragma unroll
-                for (int uu = 0; uu < UG; ++uu) red[(v * UG + uu) * 33 + lane] = acc[v][uu];
-            __syncwarp();
-            if (lane < NV) {
-                // four interleaved partial sums (a fixed order: equal windows still give bit-equal totals)
-                double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
-                const double *q = red + lane * 33;
+            for (int o = 16; o >= 1; o >>= 1) {
+                const bool hi = (lane & o) != 0;
 #pragma unroll
-                for (int l = 0; l < 32; l += 4) e0 += q[l], e1 += q[l + 1], e2 += q[l + 2], e3 += q[l + 3];
-                const double e = (e0 + e1) + (e2 + e3);
-                const int v = lane / UG, u = g * UG + lane % UG;
-                if (u < N) s_part[warp * N * N + v * N + u] = e;
+                for (int j = 0; j < o; ++j) {
+                    const double send = hi ? a[j] : a[j + o], keep = hi ? a[j + o] : a[j];
+                    a[j] = __dadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, o));
+                }
             }
-            __syncwarp();
+            if (lane < NV) {
+                const int v = lane / UG, u = g * UG + lane % UG;
+                if (u < N) s_part[warp * N * N + v * N + u] = a[0];
+            }
         }
         __syncthreads();                        // s_col and s_part complete
         if (tid < N * N) {
@@ -294,7 +304,8 @@ __global__ void __launch_bounds__(256, 2) bm_l2_tiled32_kernel(const float *__re
 #pragma unroll
             for (int x = 0; x < TS; x += 4) s0 += q[x], s1 += q[x + 1], s2 += q[x + 2], s3 += q[x + 3];
             double e = 0.0;
-            for (int w = 0; w < 8; ++w) e += s_part[w * N * N + tid];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) e += s_part[w * N * N + tid];
             s_err[tid] = ((s0 + s1) + (s2 + s3)) + e;
         }
         // the prefetched window of the next tile goes into the other buffer (nobody reads it before the next barrier)
@@ -302,17 +313,31 @@ __global__ void __launch_bounds__(256, 2) bm_l2_tiled32_kernel(const float *__re
             double *nw = s_win0 + (buf ^ 1) * NWIN;
 #pragma unroll
             for (int q = 0; q < PF; ++q) {
-                const int i = tid + q * 256;
+                const int i = tid + q * NT;
                 if (i < NWIN) nw[i] = (double)pf[q];
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            int best = 0;
-            double be = s_err[0];
-            for (int sft = 1; sft < N * N; ++sft)
-                if (s_err[sft] < be) be = s_err[sft], best = sft;                // first minimum, torch.argmin
-            flow[t] = make_float2(f.x + (float)(best % N - R), f.y + (float)(best / N - R));
+        if (warp == 0) {
+            // first minimum in raster order (torch.argmin): lane l scans shifts l, l + 32, l + 64 in that order, then the
+            // lanes combine (energy, index) pairs — smaller energy wins, equal energies keep the smaller index
+            // (a NaN energy never wins a `<` test: it counts as +inf, and a NaN at shift 0 keeps shift 0 like the serial scan)
+            int best = lane;
+            double be = (lane < N * N) ? s_err[lane] : INFINITY;
+            be = (be != be) ? INFINITY : be;
+#pragma unroll
+            for (int sft = lane + 32; sft < N * N; sft += 32)
+                if (s_err[sft] < be) be = s_err[sft], best = sft;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const double oe = __shfl_xor_sync(0xffffffffu, be, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, best, o);
+                if (oe < be || (oe == be && oi < best)) be = oe, best = oi;
+            }
+            if (lane == 0) {
+                if (s_err[0] != s_err[0]) best = 0;
+                flow[t] = make_float2(f.x + (float)(best % N - R), f.y + (float)(best / N - R));
+            }
         }
         f = fn;
     }
@@ -554,12 +579,12 @@ extern "C" int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const f
 #define HHSR_BMT(R)                                                                                                   \
     do {                                                                                                              \
         constexpr int N = 2 * R + 1, SW = 32 + 2 * R;                                                                 \
-        const size_t sm = (size_t)(2 * SW * SW + 8 * N * 3 * 33 + 8 * N * N + N * SW + 2 * N * N) * sizeof(double);   \
+        const size_t sm = (size_t)(2 * SW * SW + BM_NW * N * N + N * SW + N * N) * sizeof(double);                    \
         static std::atomic<unsigned long long> done{0};                                                               \
         ensure_dynamic_smem(bm_l2_tiled32_kernel<R>, done, sm);                                                       \
         const int ntiles = nx * ny;                                                                                   \
-        const int ctas = ntiles < 148 * 2 ? ntiles : 148 * 2;       /* persistent: 2 CTAs per SM walk the tiles */    \
-        bm_l2_tiled32_kernel<R><<<ctas, 256, sm, st>>>(ref, ref_w, mov, mov_h, mov_w, F2, nx, ntiles);                 \
+        const int ctas = ntiles < 148 * 3 ? ntiles : 148 * 3;       /* persistent: 3 CTAs per SM walk the tiles */    \
+        bm_l2_tiled32_kernel<R><<<ctas, BM_NT, sm, st>>>(ref, ref_w, mov, mov_h, mov_w, F2, nx, ntiles);               \
     } while (0)
         switch (radius) {
             case 1: HHSR_BMT(1); break;

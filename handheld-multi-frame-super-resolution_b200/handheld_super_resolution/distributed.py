@@ -309,6 +309,8 @@ def main_sharded(ref_img, comp_imgs, config, group=None, mode=None):
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:
         rank, world = 0, 1
+    if world == 1:
+        return main(ref_img, comp_imgs, config)       # nothing to exchange: the plain single-GPU path (fused finish included)
     mode = mode or os.environ.get("HHSR_SHARD_REDUCE", "reduce_scatter")
     ids = shard_frames(len(comp_imgs), rank, world)
     ahead = None
