@@ -19,6 +19,9 @@ _IP, _DP, _FP = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_float)
 # name -> argtypes (every function returns int except the two noted); mirrors include/hhsr.h
 SIGNATURES = {
     "hhsr_grey_band_mask": [_P, _I, _I, C.c_longlong, C.c_longlong, _F, _P],
+    "hhsr_grey_fft_sizes": [_I, _I, C.POINTER(_Z), C.POINTER(_Z)],
+    "hhsr_grey_fft_plan": [_P, _I, _I, _P],
+    "hhsr_grey_fft": [_P, _I, _I, _P, _P, _P, _P],
     "hhsr_pad_circular": [_P, _I, _I, _P, _I, _I, _P],
     "hhsr_gauss_downsample": [_P, _I, _I, _I, _FP, _I, _P, _I, _I, _P],
     "hhsr_grad_hessian": [_P, _I, _I, _I, _P, _P, _P, _P],

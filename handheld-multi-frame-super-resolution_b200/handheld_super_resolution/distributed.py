@@ -290,7 +290,7 @@ def broadcast_reference_frame(ref_img, group=None):
     buf = torch.empty(host.shape, dtype=host.dtype, device=torch.device("cuda", torch.cuda.current_device()))
     if dist.get_rank(group) == 0:
         buf.copy_(host, non_blocking=True)
-    wire = buf.view(torch.int16) if buf.dtype == torch.uint16 else buf
+    wire = buf.view(torch.uint8) if buf.dtype in (torch.uint16, torch.int16) else buf   # NCCL has no 16-bit integer type
     dist.broadcast(wire, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     return buf
 

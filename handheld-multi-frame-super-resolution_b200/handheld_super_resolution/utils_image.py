@@ -8,16 +8,48 @@ import torch
 from . import _lib
 
 
+_GREY_PLANS = {}      # (device, h, w) -> (plan tables on the device, bytes of the per-call work buffer) or None
+GREY_FFT_NATIVE = True   # False: always take the cuFFT route (tests compare the two)
+
+
+def _grey_plan(h, w, device):
+    """Twiddle / digit-reversal tables of the library's own grey-image FFT for an h x w frame, built once per shape and
+    device; None when the sizes do not factor into 2, 3, 5, 7 (those frames take the cuFFT route)."""
+    key = (device.index, h, w)
+    if key not in _GREY_PLANS:
+        L = _lib.lib()
+        pb, wb = C.c_size_t(), C.c_size_t()
+        rc = L.hhsr_grey_fft_sizes(h, w, C.byref(pb), C.byref(wb))
+        if rc == -2:            # HHSR_E_UNSUPPORTED
+            _GREY_PLANS[key] = None
+        elif rc != 0:
+            raise RuntimeError("hhsr_grey_fft_sizes failed (%d): %s" % (rc, L.hhsr_last_error_string().decode()))
+        else:
+            plan = torch.empty(pb.value, dtype=torch.uint8, device=device)
+            _lib.call("hhsr_grey_fft_plan", _lib.ptr(plan), h, w, _lib.stream())
+            torch.cuda.current_stream(device).synchronize()     # once per shape: other streams read the tables later
+            _GREY_PLANS[key] = (plan, wb.value)
+    return _GREY_PLANS[key]
+
+
 def compute_grey_images(img, method):
     """Raw -> grey (utils_image.py:58-115).
 
-    "FFT": the ideal half-band low-pass of Alg. 3.  The FFTs are cuFFT calls (torch.fft.rfft2 / irfft2); the
-    reference's fftshift + four masked fills + ifftshift + .real become one in-place band-mask kernel on the half
-    spectrum (hhsr_grey_band_mask), which is mathematically identical for a real input.
+    "FFT": the ideal half-band low-pass of Alg. 3.  Frames whose sizes factor into 2, 3, 5, 7 (every sensor format) go
+    through the library's own three shared-memory FFT passes (hhsr_grey_fft: rows forward, columns forward + band mask +
+    inverse, rows inverse; only the quarter of the spectrum the mask keeps is ever stored).  Other sizes: cuFFT
+    (torch.fft.rfft2 / irfft2) around the in-place band-mask kernel hhsr_grey_band_mask — the reference's fftshift +
+    four masked fills + ifftshift + .real on the half spectrum, mathematically identical for a real input.
     "decimating": 2x2 mean."""
     img = _lib.as_device(img)
     h, w = img.shape
     if method == "FFT":
+        plan = _grey_plan(h, w, img.device) if GREY_FFT_NATIVE else None
+        if plan is not None:
+            work = torch.empty(plan[1], dtype=torch.uint8, device=img.device)
+            out = torch.empty_like(img)
+            _lib.call("hhsr_grey_fft", _lib.ptr(img), h, w, _lib.ptr(plan[0]), _lib.ptr(work), _lib.ptr(out), _lib.stream())
+            return out
         spec = torch.fft.rfft2(img)
         # the 1/(h*w) of the inverse transform is folded into the mask (kept entries are scaled, the rest zeroed) and
         # the inverse runs unnormalised: one full-image multiply less per frame

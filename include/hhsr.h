@@ -44,6 +44,18 @@ const char *hhsr_last_error_string(void);
 int hhsr_grey_band_mask(float *spec, int H, int W, long long stride_y, long long stride_x, float scale,
                         hhsr_stream_t stream);
 
+/* ---- grey image, Alg. 3, as a whole (utils_image.py:82-100: fft2, fftshift, four masked fills, ifftshift, ifft2,
+ * .real) with the library's own shared-memory FFT passes: rows forward (two real rows per complex transform, only the
+ * W/4 + 1 half-spectrum columns the mask keeps are stored), columns (forward, band mask, inverse in one pass), rows
+ * inverse.  Sizes must factor into 2, 3, 5, 7 with H even (HHSR_E_UNSUPPORTED otherwise: the caller keeps the cuFFT
+ * route with hhsr_grey_band_mask for those).
+ *   hhsr_grey_fft_sizes: bytes of the two caller-owned device buffers for an H x W image (host pointers out);
+ *   hhsr_grey_fft_plan:  fills `plan` (twiddle tables rounded from float64, digit-reversal tables) once per (H, W);
+ *   hhsr_grey_fft:       out[H][W] = grey(img[H][W]); `work` is scratch (the pruned spectrum), `plan` read-only. */
+int hhsr_grey_fft_sizes(int H, int W, size_t *plan_bytes, size_t *work_bytes);
+int hhsr_grey_fft_plan(void *plan, int H, int W, hhsr_stream_t stream);
+int hhsr_grey_fft(const float *img, int H, int W, const void *plan, void *work, float *out, hhsr_stream_t stream);
+
 /* ---- Gaussian pyramid (alignment.py:74-82, utils_image.py:360-391) */
 /* circular padding of the reference grey image to a multiple of the tile size (alignment.py:26-37) */
 int hhsr_pad_circular(const float *src, int h, int w, float *dst, int hp, int wp, hhsr_stream_t stream);

@@ -71,6 +71,49 @@ def test_grey_fft_odd_sizes():
         assert d < 2e-6, (shape, d)
 
 
+@pytest.mark.parametrize("shape", [(48, 64), (96, 128), (120, 168), (350, 360), (750, 1000), (1000, 1400), (2048, 2560)])
+def test_grey_fft_native_passes(shape):
+    """The library's own FFT passes (hhsr_grey_fft: rows forward, columns + band mask, rows inverse) against the oracle
+    (float64 numpy restatement of utils_image.py:82-100) and against the cuFFT route around hhsr_grey_band_mask."""
+    import hhsr_oracle as O
+    from handheld_super_resolution import utils_image as UI
+    rng = np.random.default_rng(shape[0])
+    img = rng.random(shape).astype(np.float32)
+    assert UI._grey_plan(shape[0], shape[1], torch.device("cuda", torch.cuda.current_device())) is not None
+    got = host(UI.compute_grey_images(dev(img), "FFT"))
+    d = maxdiff(got, O.grey_fft(img))
+    record("grey_native_%dx%d" % shape, d)
+    assert d < 1e-6, (shape, d)
+    UI.GREY_FFT_NATIVE = False
+    try:
+        via_cufft = host(UI.compute_grey_images(dev(img), "FFT"))
+    finally:
+        UI.GREY_FFT_NATIVE = True
+    assert maxdiff(got, via_cufft) < 1e-6
+
+
+def test_grey_fft_native_benchmark_shapes():
+    """12 MP and 50 MP frames (the benchmark shapes): native passes vs the cuFFT route, and the input is left untouched."""
+    from handheld_super_resolution import utils_image as UI
+    from handheld_super_resolution.synthetic import synth_burst
+    for (H, W) in [(3000, 4000), (6144, 8192)]:
+        burst, _ = synth_burst(2, H, W, seed=3, device="cuda", as_numpy=False)
+        img = burst[1]
+        keep = img.clone()
+        got = UI.compute_grey_images(img, "FFT")
+        assert torch.equal(img, keep)
+        UI.GREY_FFT_NATIVE = False
+        try:
+            want = UI.compute_grey_images(img, "FFT")
+        finally:
+            UI.GREY_FFT_NATIVE = True
+        d = float((got - want).abs().max())
+        record("grey_native_vs_cufft_%dx%d" % (H, W), d)
+        assert d < 1e-6, ((H, W), d)
+        del burst, img, keep, got, want
+        torch.cuda.empty_cache()
+
+
 def test_pyramid_and_init_alignment(tiny):
     from handheld_super_resolution.alignment import init_alignment
     cfg = attr_cfg(tiny["cfg_json"])
