@@ -138,6 +138,75 @@ __global__ void __launch_bounds__(DBX *DBY) gauss_downsample_kernel(const float 
     dst[(size_t)oy * w2 + ox] = acc;
 }
 
+
+// The two factors of the default pyramid (2 with 9 taps, 4 with 17 taps) as a column-streaming kernel: a thread owns one
+// INPUT column of the CTA's strip and walks down it with the 2R + 1 rows of the y pass in registers (every input sample
+// is loaded exactly once, coalesced across the warp, all loads of a strip independent of each other); the RY rows of
+// y-pass results go to shared memory once, then the x pass reads its 2R + 1 neighbours as aligned 8- / 16-byte vectors
+// (conflict-free).  Same arithmetic, same order as the generic kernel: acc = fma(g[a], v[a], acc), a ascending, y pass
+// then x pass — the outputs are bit-identical.
+template <int F, int RR, int RY>
+__global__ void __launch_bounds__(256) gauss_downsample_stream_kernel(const float *__restrict__ src, int h, int w, Taps taps,
+                                                                      float *__restrict__ dst, int h2, int w2) {
+    constexpr int K = 2 * RR + 1, NT = 256, OX = (NT - 2 * RR) / F;
+    __shared__ __align__(16) float tmp[RY][NT];
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * OX, oy0 = blockIdx.y * RY;
+    const int gx = ox0 * F + tid, iy0 = oy0 * F;
+    const float *p = src + (size_t)iy0 * w + gx;
+    const bool colok = gx < w;
+    float win[K];
+#pragma unroll
+    for (int a = 0; a < K - F; ++a) win[a + F] = (colok && iy0 + a < h) ? __ldg(p + (size_t)a * w) : 0.f;
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+#pragma unroll
+        for (int a = 0; a < K - F; ++a) win[a] = win[a + F];
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+            const int row = F * r + K - F + j;
+            win[K - F + j] = (colok && iy0 + row < h) ? __ldg(p + (size_t)row * w) : 0.f;
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < K; ++a) acc = fmaf(taps.g[a], win[a], acc);
+        tmp[r][tid] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < RY * OX; idx += NT) {
+        const int r = idx / OX, oxl = idx - r * OX;
+        const int ox = ox0 + oxl, oy = oy0 + r;
+        if (ox >= w2 || oy >= h2) continue;
+        const float *rowp = &tmp[r][F * oxl];
+        float v[K];
+        if (F == 2) {
+#pragma unroll
+            for (int j = 0; j < K / 2; ++j) {
+                const float2 t = *reinterpret_cast<const float2 *>(rowp + 2 * j);
+                v[2 * j] = t.x, v[2 * j + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K / 4; ++j) {
+                const float4 t = *reinterpret_cast<const float4 *>(rowp + 4 * j);
+                v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+            }
+        }
+        v[K - 1] = rowp[K - 1];
+        float acc = 0.f;
+#pragma unroll
+        for (int b = 0; b < K; ++b) acc = fmaf(taps.g[b], v[b], acc);
+        dst[(size_t)oy * w2 + ox] = acc;
+    }
+}
+
+template <int F, int RR, int RY>
+static void launch_stream(const float *src, int h, int w, const Taps &t, float *dst, int h2, int w2, cudaStream_t st) {
+    constexpr int OX = (256 - 2 * RR) / F;
+    dim3 grid(ceil_div(w2, OX), ceil_div(h2, RY));
+    gauss_downsample_stream_kernel<F, RR, RY><<<grid, 256, 0, st>>>(src, h, w, t, dst, h2, w2);
+}
+
 }  // namespace hhsr
 
 using namespace hhsr;
@@ -186,9 +255,12 @@ extern "C" int hhsr_gauss_downsample(const float *src, int h, int w, int factor,
     dim3 block(DBX, DBY), grid(ceil_div(w2, DBX), ceil_div(h2, DBY));
     cudaStream_t st = (cudaStream_t)stream;
     if (factor == 2 && radius == 4) {
-        gauss_downsample_kernel<2, 4><<<grid, block, smem, st>>>(src, h, w, factor, radius, t, dst, h2, w2);
+        // strips of 32 output rows; short strips when the level is too small to fill the GPU otherwise
+        if ((long long)ceil_div(w2, 124) * ceil_div(h2, 32) >= 296) launch_stream<2, 4, 32>(src, h, w, t, dst, h2, w2, st);
+        else launch_stream<2, 4, 8>(src, h, w, t, dst, h2, w2, st);
     } else if (factor == 4 && radius == 8) {
-        gauss_downsample_kernel<4, 8><<<grid, block, smem, st>>>(src, h, w, factor, radius, t, dst, h2, w2);
+        if ((long long)ceil_div(w2, 60) * ceil_div(h2, 16) >= 148) launch_stream<4, 8, 16>(src, h, w, t, dst, h2, w2, st);
+        else launch_stream<4, 8, 4>(src, h, w, t, dst, h2, w2, st);
     } else {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(gauss_downsample_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
