@@ -13,6 +13,7 @@ inside the timed region).  One JSON line on stdout (rank 0).
 import argparse
 import json
 import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # before the CUDA context exists (see handheld_super_resolution/__init__.py)
 import subprocess
 import sys
 import threading
@@ -72,31 +73,80 @@ def workload_config(wl_name, wl, n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML queried in-process
+    every 50 ms from a thread (nvidia_ml_py), falling back to one resident `nvidia-smi -lms` process when NVML cannot be
+    loaded.  (A resident nvidia-smi polling at 10 Hz was seen to stall the launching thread of short legs at random;
+    the in-process queries are three cheap calls per sample.)"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip() != ""]
+        if ids and all(v.isdigit() for v in ids) and self.index < len(ids):
+            return int(ids[self.index])
+        return self.index
 
     def start(self):
+        if os.environ.get("HHSR_BENCH_SAMPLER", "nvml") == "off":
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+            if os.environ.get("HHSR_BENCH_SAMPLER", "nvml") != "nvml":
+                raise RuntimeError("nvidia-smi requested")
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index()))
+            threading.Thread(target=self._poll_nvml, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        R = nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown
+        bits = [("hw_slowdown", R),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0))),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0))),
+                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0)))]
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = reasons_fn(h)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = 0.0
+                self.rows.append((time.perf_counter(), [str(sm), str(mx), "%.2f" % pw] + ["Active" if (mask & b) else "Not Active" for _, b in bits]))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.proc is None and self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sampler (nvml and nvidia-smi unavailable or switched off)"]}
         time.sleep(0.15)
-        self.proc.terminate()
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
         rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
@@ -104,7 +154,8 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows),
+                "source": "nvml in-process, 50 ms" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 def measured_peak_gbs():
@@ -364,14 +415,18 @@ def run_cuda_arm(args, wl, wl_name):
         if not pipelined:
             done.synchronize()
 
+    trace = []      # HHSR_BENCH_TRACE: (ms inside main(), ms waiting for the host buffer, cudaMalloc calls so far) per e2e step
+
     def step_e2e(pipelined=True, u16=False):
         """Host burst in, host image out.  The D2H of the 48 MP result runs on its own stream into one of two pinned
         buffers, so it overlaps the NEXT burst's compute (steady-state throughput of back-to-back bursts); every
         copy still happens inside the timed region, which ends with a full device synchronisation."""
+        tm0 = time.perf_counter()
         if u16:
             out, dbg = main_sharded(burst_u16[0], burst_u16[1:], cfg_u16)
         else:
             out, dbg = main_sharded(burst_host[0], burst_host[1:], cfg)
+        tm1 = time.perf_counter()
         # who copies what to the host: with the row-sharded merge every rank owns a slice of the image and sends it over
         # its own PCIe link into the shared host image; otherwise rank 0 holds the whole image
         rows = dbg.get("rows") if isinstance(dbg, dict) else None
@@ -380,6 +435,9 @@ def run_cuda_arm(args, wl, wl_name):
             d2h_state["k"] += 1
             if d2h_state["events"][k] is not None:
                 d2h_state["events"][k].synchronize()          # buffer k free again (its previous copy finished)
+            if os.environ.get("HHSR_BENCH_TRACE"):
+                trace.append((round((tm1 - tm0) * 1e3, 1), round((time.perf_counter() - tm1) * 1e3, 1),
+                              torch.cuda.memory_stats().get("num_device_alloc", 0)))
             ready = torch.cuda.Event()
             ready.record()
             with torch.cuda.stream(d2h_stream if pipelined else torch.cuda.current_stream()):
@@ -406,8 +464,16 @@ def run_cuda_arm(args, wl, wl_name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
+        stamps = [time.perf_counter()]
         for _ in range(steps):
             fn()
+            stamps.append(time.perf_counter())
+        if os.environ.get("HHSR_BENCH_TRACE"):       # host-side enqueue time of every step of this leg
+            if trace:
+                print("   (main ms, buffer-wait ms, mallocs):", trace[-steps:], file=sys.stderr)
+                del trace[:]
+            print("host ms per step:", [round((b - a) * 1e3, 1) for a, b in zip(stamps, stamps[1:])],
+                  "cudaMalloc calls:", torch.cuda.memory_stats().get("num_device_alloc", 0), file=sys.stderr)
         torch.cuda.current_stream().wait_stream(d2h_stream)      # the last result copy belongs to the timed region
         e1.record()
         barrier()
@@ -417,6 +483,11 @@ def run_cuda_arm(args, wl, wl_name):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps, t0, t1
 
+    if os.environ.get("HHSR_BENCH_NOGC"):
+        import gc
+        gc.collect()
+        gc.freeze()
+        gc.disable()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     merge_events.clear()
@@ -444,16 +515,16 @@ def run_cuda_arm(args, wl, wl_name):
         ms_post = ms_post_lat = None
         t2 = t1
     else:
-        for _ in range(2):
+        for _ in range(max(args.warmup, 3)):
             step_e2e()
         ms_e2e, _, t2 = timed(step_e2e, args.steps)
         ms_lat, _, t2 = timed(lambda: step_e2e(pipelined=False), max(2, args.steps // 2))   # one burst at a time, host-synchronous
-        for _ in range(2):
+        for _ in range(max(args.warmup, 3)):
             step_e2e(u16=True)
         ms_u16, _, t2 = timed(lambda: step_e2e(u16=True), args.steps)
         ms_post = ms_post_lat = None
         if world == 1:
-            for _ in range(2):
+            for _ in range(max(args.warmup, 3)):
                 step_e2e_post()
             ms_post, _, t2 = timed(step_e2e_post, args.steps)
             ms_post_lat, _, t2 = timed(lambda: step_e2e_post(pipelined=False), max(2, args.steps // 2))

@@ -111,7 +111,10 @@ __global__ void upscale_flow_kernel(const float2 *__restrict__ in, int ny_in, in
 // L2 block matching.  E(v,u) = sum m^2 - 2 sum ref*m, accumulated in float64 so the argmin is the exact one
 // (the reference obtains the same quantity through float32 FFTs; only exact/near ties can differ).
 // ---------------------------------------------------------------------------------------------------------
-template <int TS>
+// METRIC 1 is the L1 level as the reference INTENDS it (block_matching.py:78-345: sum |ref - m| over the tile, moving
+// samples outside the frame read as zero, first minimum, flow <- rint(flow) + shift); the compiled reference never
+// reaches it (bm_l1_compat_kernel below), so it is offered behind an explicit switch only.
+template <int TS, int METRIC = 0>
 __global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ ref, int ref_w, const float *__restrict__ mov,
                                                     int mov_h, int mov_w, float2 *__restrict__ flow, int nx, int r) {
     extern __shared__ double bsm[];   // tile and window are staged as float64: the inner loop is LDS.64 + DFMA
@@ -125,12 +128,15 @@ __global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ re
     const float2 f = flow[(size_t)ty * nx + tx];
     const int fx = (int)rintf(f.x), fy = (int)rintf(f.y);                       // flow.round(), :352
     for (int p = threadIdx.x; p < TS * TS; p += NT)
-        s_ref[p] = -2.0 * (double)__ldg(ref + (size_t)(ty * TS + p / TS) * ref_w + tx * TS + p % TS);
+        s_ref[p] = (METRIC ? 1.0 : -2.0) * (double)__ldg(ref + (size_t)(ty * TS + p / TS) * ref_w + tx * TS + p % TS);
     for (int yy0 = threadIdx.x / 32; yy0 < sw; yy0 += NT / 32) {               // one warp per window row
-        const int yy = min(max(ty * TS + fy - r + yy0, 0), mov_h - 1);          // clamp, :368-369
+        const int yr = ty * TS + fy - r + yy0;
+        const int yy = min(max(yr, 0), mov_h - 1);                              // clamp, :368-369
         for (int xx0 = threadIdx.x & 31; xx0 < sw; xx0 += 32) {
-            const int xx = min(max(tx * TS + fx - r + xx0, 0), mov_w - 1);
-            s_win[yy0 * sw + xx0] = (double)__ldg(mov + (size_t)yy * mov_w + xx);
+            const int xr = tx * TS + fx - r + xx0;
+            const int xx = min(max(xr, 0), mov_w - 1);
+            const bool inside = yr == yy && xr == xx;
+            s_win[yy0 * sw + xx0] = (METRIC && !inside) ? 0.0 : (double)__ldg(mov + (size_t)yy * mov_w + xx);   // L1: zero fill, :112-121
         }
     }
     __syncthreads();
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ re
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 const double m = wp[c];
-                e = fma(m, m + rp[c], e);                                        // m^2 - 2 ref m
+                e = METRIC ? e + fabs(rp[c] - m) : fma(m, m + rp[c], e);         // |ref - m|  or  m^2 - 2 ref m
             }
             wp += RPP * sw;
             rp += RPP * TS;
@@ -161,7 +167,10 @@ __global__ void __launch_bounds__(256) bm_l2_kernel(const float *__restrict__ re
         double be = s_err[0];
         for (int s = 1; s < n * n; ++s)
             if (s_err[s] < be) be = s_err[s], best = s;                          // first minimum, torch.argmin
-        flow[(size_t)ty * nx + tx] = make_float2(f.x + (float)(best % n - r), f.y + (float)(best / n - r));
+        if (METRIC)
+            flow[(size_t)ty * nx + tx] = make_float2((float)(fx + best % n - r), (float)(fy + best / n - r));   // rint(flow) + shift
+        else
+            flow[(size_t)ty * nx + tx] = make_float2(f.x + (float)(best % n - r), f.y + (float)(best / n - r));
     }
 }
 
@@ -449,7 +458,10 @@ __global__ void __launch_bounds__(NT) ica_kernel(const float *__restrict__ ref, 
 // the two block-wide sums of an iteration are finished redundantly by every thread from double-buffered per-warp
 // partials (one barrier per iteration instead of two, no serial solve by thread 0).  Same per-pixel arithmetic as
 // ica_kernel<32, 1, 256>; only the summation order of B differs (float32 rounding level).
-template <bool VEC4>
+// GRAD: gradx / grady are not read — they are the central differences of `ref` (what hhsr_grad_hessian writes, ICA.py:20-21:
+// right - left, down - up, zero outside) and are re-formed from four rows of ref: 96 MB less to read per 12 MP frame for
+// identical values.
+template <bool VEC4, bool GRAD = false>
 __global__ void __launch_bounds__(128) ica32_kernel(const float *__restrict__ ref, const float *__restrict__ gradx,
                                                     const float *__restrict__ grady, int ref_w, const float4 *__restrict__ hessian,
                                                     const float *__restrict__ mov, int h, int w, float2 *__restrict__ flow, int nx,
@@ -465,6 +477,31 @@ __global__ void __launch_bounds__(128) ica32_kernel(const float *__restrict__ re
     const int lx = (tid & 7) * 4, ly = (tid >> 3) * 2;
     const int gx0 = px * TS + lx, gy0 = py * TS + ly;
     float rc[2][4], gx[2][4], gy[2][4];
+    if (GRAD) {
+        const int ref_h = (int)gridDim.y * TS;      // the launcher requires ny * ts == ref_h and nx * ts == ref_w in this mode
+        float rows[4][6];                           // ref rows gy0-1 .. gy0+2, columns gx0-1 .. gx0+4 (zero outside)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int y = gy0 - 1 + r;
+            const bool yin = y >= 0 && y < ref_h;
+            const size_t o = (size_t)(yin ? y : gy0) * ref_w + gx0;
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(ref + o));
+            rows[r][1] = yin ? a.x : 0.f, rows[r][2] = yin ? a.y : 0.f, rows[r][3] = yin ? a.z : 0.f, rows[r][4] = yin ? a.w : 0.f;
+            rows[r][0] = rows[r][5] = 0.f;
+            if (r == 1 || r == 2) {                 // the side columns only feed gradx of this thread's own two rows
+                rows[r][0] = gx0 > 0 ? __ldg(ref + o - 1) : 0.f;
+                rows[r][5] = gx0 + 4 < ref_w ? __ldg(ref + o + 4) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                rc[r][k] = rows[r + 1][k + 1];
+                gx[r][k] = rows[r + 1][k + 2] - rows[r + 1][k];
+                gy[r][k] = rows[r + 2][k + 1] - rows[r][k + 1];
+            }
+    } else
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const size_t o = (size_t)(gy0 + r) * ref_w + gx0;
@@ -605,6 +642,34 @@ extern "C" int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const f
     return launch_status("bm_l2_search");
 }
 
+extern "C" int hhsr_bm_l1_search(const float *ref, int ref_h, int ref_w, const float *mov, int mov_h, int mov_w,
+                                 float *flow, int ny, int nx, int ts, int radius, hhsr_stream_t stream) {
+    HHSR_REQUIRE(ref && mov && flow, "null pointer");
+    HHSR_REQUIRE(ny > 0 && nx > 0 && mov_h > 0 && mov_w > 0, "non-positive size");
+    if (!(ts == 16 || ts == 32 || ts == 64))
+        return unsupported("L1 local search tile size must be 16, 32 or 64 (block_matching.py:86-93)");
+    HHSR_REQUIRE(radius >= 0 && radius <= 8, "search radius must be in [0, 8]");
+    HHSR_REQUIRE(ny * ts <= ref_h && nx * ts <= ref_w, "tile grid exceeds the reference level");
+    const int sw = ts + 2 * radius, n = 2 * radius + 1;
+    const size_t smem = (size_t)(ts * ts + sw * sw + n * n) * sizeof(double);
+    dim3 grid(nx, ny);
+    cudaStream_t st = (cudaStream_t)stream;
+    float2 *F2 = reinterpret_cast<float2 *>(flow);
+#define HHSR_BM1(TS)                                                                                          \
+    do {                                                                                                     \
+        static std::atomic<unsigned long long> done{0};                                                      \
+        if (smem > 48 * 1024) ensure_dynamic_smem(bm_l2_kernel<TS, 1>, done, smem);                           \
+        bm_l2_kernel<TS, 1><<<grid, 256, smem, st>>>(ref, ref_w, mov, mov_h, mov_w, F2, nx, radius);          \
+    } while (0)
+    switch (ts) {
+        case 16: HHSR_BM1(16); break;
+        case 32: HHSR_BM1(32); break;
+        default: HHSR_BM1(64); break;
+    }
+#undef HHSR_BM1
+    return launch_status("bm_l1_search");
+}
+
 extern "C" int hhsr_bm_l1_compat(float *flow, int n, hhsr_stream_t stream) {
     HHSR_REQUIRE(flow && n > 0, "null pointer or empty flow");
     bm_l1_compat_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(flow, n);
@@ -614,7 +679,12 @@ extern "C" int hhsr_bm_l1_compat(float *flow, int n, hhsr_stream_t stream) {
 extern "C" int hhsr_ica(const float *ref, const float *gradx, const float *grady, int ref_h, int ref_w,
                         const float *hessian, const float *mov, int mov_h, int mov_w, float *flow, int ny, int nx, int ts,
                         int n_iter, hhsr_stream_t stream) {
-    HHSR_REQUIRE(ref && gradx && grady && hessian && mov && flow, "null pointer");
+    HHSR_REQUIRE(ref && hessian && mov && flow, "null pointer");
+    // gradx == grady == NULL: the gradients are the central differences of ref (hhsr_grad_hessian) and are re-formed on the fly
+    const bool on_the_fly = !gradx && !grady;
+    HHSR_REQUIRE(on_the_fly || (gradx && grady), "gradx and grady must both be given or both be null");
+    if (on_the_fly && !(ts == 32 && ny * ts == ref_h && nx * ts == ref_w && ref_w % 4 == 0 && (uintptr_t)ref % 16 == 0))
+        return unsupported("on-the-fly gradients need tile size 32, a reference level that is a whole number of tiles and 16-byte aligned rows");
     HHSR_REQUIRE(ny > 0 && nx > 0 && mov_h > 0 && mov_w > 0 && n_iter > 0, "non-positive size");
     HHSR_REQUIRE(ny * ts <= ref_h && nx * ts <= ref_w, "tile grid exceeds the reference level");
     HHSR_REQUIRE((uintptr_t)hessian % 16 == 0 && (uintptr_t)flow % 8 == 0, "hessian/flow misaligned");
@@ -626,7 +696,9 @@ extern "C" int hhsr_ica(const float *ref, const float *gradx, const float *grady
         case 8: ica_kernel<8, 0, 64><<<grid, 64, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter); break;
         case 16: ica_kernel<16, 1, 256><<<grid, 256, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter); break;
         case 32:
-            if (ref_w % 4 == 0 && (uintptr_t)ref % 16 == 0 && (uintptr_t)gradx % 16 == 0 && (uintptr_t)grady % 16 == 0)
+            if (!gradx && !grady)
+                ica32_kernel<true, true><<<grid, 128, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter);
+            else if (ref_w % 4 == 0 && (uintptr_t)ref % 16 == 0 && (uintptr_t)gradx % 16 == 0 && (uintptr_t)grady % 16 == 0)
                 ica32_kernel<true><<<grid, 128, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter);
             else
                 ica32_kernel<false><<<grid, 128, 0, st>>>(ref, gradx, grady, ref_w, H4, mov, mov_h, mov_w, F2, nx, n_iter);

@@ -28,6 +28,7 @@ SIGNATURES = {
     "hhsr_upscale_flow": [_P, _I, _I, _P, _I, _I, _I, _F, _I, _P],
     "hhsr_bm_l2_search": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P],
     "hhsr_bm_l1_compat": [_P, _I, _P],
+    "hhsr_bm_l1_search": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P],
     "hhsr_ica": [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _I, _I, _I, _I, _P],
     "hhsr_estimate_kernels": [_P, _I, _I, _D, _D, _D, _D, _D, _D, _D, _D, _I, _P, _P],
     "hhsr_gat": [_P, _Z, _D, _D, _P, _P],

@@ -23,13 +23,23 @@ def align_lvl_block_matching_L2(tyled_pyr_lvl, ref_fft_lvl, moving_lvl, alignmen
               ny, nx, int(ts), int(radius), _lib.stream())
 
 
+_WARNED = set()
+
+
 def align_lvl_block_matching_L1(ref_lvl, moving_lvl, alignments, l, config):
-    """The L1 level as the compiled reference executes it (block_matching.py:78-345): its SAD search never
-    updates the shift (`if err < min` with err = +inf), so the net effect is alignments <- rint(alignments)
-    (confirmed on B200 for tile sizes 32 and 64 by baseline/probe_reference.py).  Tile size 16 is
-    undefined behaviour upstream (a data race) and is given the same well-defined semantics here."""
-    ts = config.block_matching.tuning.tile_sizes[l]
-    radius = config.block_matching.tuning.search_radii[l]
+    """The L1 level (block_matching.py:78-345).
+
+    Default (`block_matching.tuning.l1_compat` absent or true): what the compiled reference EXECUTES — its SAD search
+    never updates the shift (`if err < min` with err = +inf), so the net effect is alignments <- rint(alignments)
+    (confirmed on B200 for tile sizes 32 and 64 by baseline/probe_reference.py).  Tile size 16 is undefined
+    behaviour upstream (a data race) and is given the same well-defined semantics here.  A one-time warning
+    says that search_radii[l] is ignored on this path.
+
+    `l1_compat: false`: what the reference INTENDS — an exhaustive sum |ref - moving| search over (2r+1)^2 shifts around
+    rint(alignment), zero outside the frame, first minimum (hhsr_bm_l1_search).  Not parity with upstream's outputs."""
+    tuning = config.block_matching.tuning
+    ts = tuning.tile_sizes[l]
+    radius = tuning.search_radii[l]
     if ts not in (16, 32, 64):
         raise NotImplementedError("L1 local search kernel for tile size {} not implemented".format(ts))
     if ts == 16:
@@ -37,4 +47,18 @@ def align_lvl_block_matching_L1(ref_lvl, moving_lvl, alignments, l, config):
     if ts == 64:
         assert 2 * radius <= 16, f"Cant handle search radius {radius} with tile size {ts} in L1 local search kernel."
     assert alignments.is_cuda and alignments.is_contiguous() and alignments.dtype == torch.float32
-    _lib.call("hhsr_bm_l1_compat", _lib.ptr(alignments), alignments.numel(), _lib.stream())
+    compat = tuning.get("l1_compat", True) if hasattr(tuning, "get") else getattr(tuning, "l1_compat", True)
+    if compat:
+        if radius > 0 and "l1" not in _WARNED:
+            _WARNED.add("l1")
+            import warnings
+            warnings.warn("L1 block-matching level: reproducing the compiled reference, which does not search (flow <- "
+                          "rint(flow), search radius ignored); set block_matching.tuning.l1_compat = false for the intended "
+                          "SAD search", stacklevel=2)
+        _lib.call("hhsr_bm_l1_compat", _lib.ptr(alignments), alignments.numel(), _lib.stream())
+        return
+    ny, nx, _ = alignments.shape
+    rh, rw = ref_lvl.shape
+    mh, mw = moving_lvl.shape
+    _lib.call("hhsr_bm_l1_search", _lib.ptr(ref_lvl), rh, rw, _lib.ptr(moving_lvl), mh, mw, _lib.ptr(alignments),
+              ny, nx, int(ts), int(radius), _lib.stream())

@@ -36,6 +36,27 @@ def _copy_stream(device):
     return s
 
 
+_INFLIGHT = {}      # device index -> events marking the end of the bursts enqueued so far (most recent last)
+MAX_BURSTS_IN_FLIGHT = int(os.environ.get("HHSR_MAX_BURSTS_IN_FLIGHT", "2"))
+
+
+def _throttle_host(device):
+    """main() only enqueues work; a caller that loops over bursts without ever reading a result would queue work without
+    bound (the driver then blocks the launching thread until its queues DRAIN, which leaves the GPU idle while they are
+    refilled — measured: one 90 ms stall every few bursts).  Entering main() therefore waits until at most
+    MAX_BURSTS_IN_FLIGHT earlier bursts are still running on this device: no cost in steady state, the host just stays at
+    most that far ahead of the GPU."""
+    q = _INFLIGHT.setdefault(device.index, [])
+    while len(q) >= max(1, MAX_BURSTS_IN_FLIGHT):
+        q.pop(0).synchronize()
+
+
+def _burst_enqueued(device):
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    _INFLIGHT.setdefault(device.index, []).append(ev)
+
+
 _ALIGN_STREAMS = {}
 
 
@@ -87,29 +108,45 @@ class FrameFeeder:
     SLOTS = int(os.environ.get("HHSR_STAGING_SLOTS", "12"))
     _RINGS = {}     # (device, compute stream, role, shape, dtype, slot) -> [buffer, event "slot free"]: staging buffers live
                     # across bursts, so the first uploads of burst i+1 need not wait for the compute stream to drain burst i
+    _CURSORS = {}   # (device, compute stream, role, shape, dtype) -> frames staged so far (ring position, kept across bursts)
 
     def __init__(self, frames, ids, config, device, role="comp", extra_slots=0):
         self.frames, self.ids, self.config, self.device, self.role = frames, list(ids), config, device, role
-        self.SLOTS = FrameFeeder.SLOTS + extra_slots     # frames waiting in a merge batch keep their slots
+        # frames waiting in a merge batch keep their slots; the reference frame is cloned at once (two slots: bursts overlap)
+        self.SLOTS = 2 if role == "ref" else FrameFeeder.SLOTS + extra_slots
         self.compute = torch.cuda.current_stream(device)
         self.copy = _copy_stream(device)
         self.norm = None
         self.ready = {}
 
-    def _slot(self, host, k):
-        key = (self.device.index, self.compute.cuda_stream, self.role, tuple(host.shape), host.dtype, k % self.SLOTS)
+    def _slot(self, host):
+        """Next staging buffer of the ring for frames shaped like `host`.  The ring position is kept ACROSS bursts: the
+        first frames of burst i + 1 take the buffers released longest ago (early frames of burst i, merged long since)
+        instead of the ones its last merge batch still holds, so their uploads overlap the tail of burst i."""
+        ring = (self.device.index, self.compute.cuda_stream, self.role, tuple(host.shape), host.dtype)
+        pos = FrameFeeder._CURSORS.get(ring, 0)
+        FrameFeeder._CURSORS[ring] = pos + 1
+        key = ring + (pos % self.SLOTS,)
         slot = FrameFeeder._RINGS.get(key)
         if slot is None:
-            buf = torch.empty(host.shape, dtype=host.dtype, device=self.device)   # compute-stream pool
-            ev = torch.cuda.Event()
-            ev.record(self.compute)        # the block may still be in use by earlier work of the compute stream
-            if len(FrameFeeder._RINGS) > 64:      # shapes changed many times: drop the old staging buffers
+            # first touch of this ring (or a longer ring than before): allocate EVERY missing slot now.  A fresh block of
+            # the compute-stream pool may still be in use by work already queued there, so its first upload has to wait
+            # for the compute stream to reach this point — once, not once per burst while the ring fills up
+            if len(FrameFeeder._RINGS) > 256:      # shapes changed many times: drop the old staging buffers
                 FrameFeeder._RINGS.clear()
-            slot = FrameFeeder._RINGS[key] = [buf, ev]
+            ev = torch.cuda.Event()
+            for i in range(self.SLOTS):
+                if ring + (i,) not in FrameFeeder._RINGS:
+                    # uint16 sensor counts: the slot also owns the float32 frame they are normalised into, so a steady
+                    # stream of bursts allocates nothing (a cudaMalloc in the middle of a burst stalls the whole pipeline)
+                    norm = torch.empty(host.shape, dtype=torch.float32, device=self.device) if host.dtype == torch.uint16 else None
+                    FrameFeeder._RINGS[ring + (i,)] = [torch.empty(host.shape, dtype=host.dtype, device=self.device), ev, norm]
+            ev.record(self.compute)
+            slot = FrameFeeder._RINGS[key]
         return slot
 
     def owns(self, t):
-        return any(t is s[0] for s in FrameFeeder._RINGS.values())
+        return any(t is s[0] or t is s[2] for s in FrameFeeder._RINGS.values())
 
     def _stage(self, k):
         """Enqueue the H2D copy of the k-th frame of `ids` (no-op for device frames)."""
@@ -120,7 +157,7 @@ class FrameFeeder:
             self.ready[k] = (frame, None)
             return
         host = _host_tensor(frame)
-        slot = self._slot(host, k)
+        slot = self._slot(host)
         buf = slot[0]
         with torch.cuda.stream(self.copy):
             self.copy.wait_event(slot[1])                 # previous user of this slot is done
@@ -136,16 +173,16 @@ class FrameFeeder:
         item = self.ready[k]
         if item[1] is None:
             return self._normalised(item[0])
-        buf, ev, key = item
+        buf, ev, slot = item
         self.compute.wait_event(ev)
-        return self._normalised(buf)
+        return self._normalised(buf, slot[2])
 
-    def _normalised(self, t):
+    def _normalised(self, t, out=None):
         if t.dtype == torch.uint16:
             if self.norm is None:
                 from .utils_dng import RawNormalization
                 self.norm = RawNormalization.from_config(self.config)
-            return self.norm.apply(t)
+            return self.norm.apply(t, out=out)
         return t if t.dtype == torch.float32 else t.to(torch.float32)
 
     def release(self, k):
@@ -176,6 +213,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
     `align_ahead`: alignment chains in flight on side streams (default ALIGN_AHEAD = 1)."""
     verbose_2 = config.verbose >= 2
     grey_method = config.grey_method
+    _throttle_host(torch.device("cuda", torch.cuda.current_device()))
     if config.mode != "bayer":
         raise NotImplementedError("only bayer mode is supported (grey mode is broken upstream, SURVEY Q14)")
     init_alignment_ = timer(init_alignment, verbose_2, "\nInitializing alignment", "Alignment initialized (Total)")
@@ -320,6 +358,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
         _mark("fused_reduce_merge_ref")
         if accumulate_r:
             debug_dict["accumulated robustness"] = accumulated_r
+        _burst_enqueued(dev)
         return num, debug_dict
     if reduce_fn is not None:
         res = reduce_fn(num, den, accumulated_r)
@@ -342,6 +381,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
         print(s, " " * (50 - len(s)), ": ", round((time.perf_counter() - t1), 2), "seconds")
     if accumulate_r:
         debug_dict["accumulated robustness"] = accumulated_r
+    _burst_enqueued(dev)
     return num, debug_dict
 
 

@@ -83,10 +83,19 @@ int hhsr_bm_l2_search(const float *ref, int ref_h, int ref_w, const float *mov, 
 /* ---- "L1" level as the compiled reference executes it (block_matching.py:78-345): the SAD search
  * result is discarded and flow <- rint(flow) (half to even).  n = ny*nx*2 floats. */
 int hhsr_bm_l1_compat(float *flow, int n, hhsr_stream_t stream);
+/* ---- the L1 level as the reference INTENDS it (block_matching.py:78-345, never reached by the compiled reference —
+ * SURVEY Q1; selected by block_matching.tuning.l1_compat = false only): per tile, exhaustive search of sum |ref - m|
+ * over (2r+1)^2 integer shifts around rint(flow), moving samples outside the frame read as 0, sums in float64, first
+ * minimum in v-major order; flow <- rint(flow) + (u*, v*) in place.  ts in {16,32,64}, radius <= 8. */
+int hhsr_bm_l1_search(const float *ref, int ref_h, int ref_w, const float *mov, int mov_h, int mov_w,
+                      float *flow, int ny, int nx, int ts, int radius, hhsr_stream_t stream);
 
 /* ---- ICA / Lucas-Kanade refinement (ICA.py:78-481): n_iter Gauss-Newton steps per tile, in place on flow.
  * ts selects the reference kernel being reproduced: 8 (clamped sampling, fp64 1/det), 16 and 32 (zero fill),
- * 64 (zero fill + sliding-window row quirk). */
+ * 64 (zero fill + sliding-window row quirk).
+ * gradx == grady == NULL (ts 32, reference level a whole number of tiles, ref_w % 4 == 0): the gradients are taken to be the
+ * central differences of `ref` that hhsr_grad_hessian writes and are re-formed inside the kernel (same values, two full
+ * planes less to read). */
 int hhsr_ica(const float *ref, const float *gradx, const float *grady, int ref_h, int ref_w,
              const float *hessian, const float *mov, int mov_h, int mov_w, float *flow, int ny, int nx, int ts,
              int n_iter, hhsr_stream_t stream);

@@ -209,6 +209,37 @@ def bm_l1_compiled(flow):
     return np.rint(flow).astype(F32)
 
 
+def bm_l1_intended(ref, mov, flow, ts, r, return_margin=False):
+    """The L1 level as block_matching.py:78-345 intends it (NOT what the compiled reference does, see bm_l1_compiled):
+    E[v,u] = sum |ref - m| over the tile, m read at rint(flow) + (u, v) with ZERO outside the frame (:208-216), float64
+    sums, first minimum in v-major order, flow <- rint(flow) + (u*, v*)."""
+    ny, nx = flow.shape[:2]
+    hm, wm = mov.shape
+    f = np.rint(flow).astype(np.int64)
+    reft = tile_view(ref.astype(F64), ts, ny, nx)
+    n = 2 * r + 1
+    E = np.empty((ny, nx, n, n), F64)
+    ys = (np.arange(ny) * ts)[:, None, None, None] + np.arange(ts)[None, None, :, None]
+    xs = (np.arange(nx) * ts)[None, :, None, None] + np.arange(ts)[None, None, None, :]
+    movd = mov.astype(F64)
+    for v in range(-r, r + 1):
+        yr = ys + f[..., 1][:, :, None, None] + v
+        for u in range(-r, r + 1):
+            xr = xs + f[..., 0][:, :, None, None] + u
+            inside = (yr >= 0) & (yr < hm) & (xr >= 0) & (xr < wm)
+            m = np.where(inside, movd[np.clip(yr, 0, hm - 1), np.clip(xr, 0, wm - 1)], 0.0)
+            E[:, :, v + r, u + r] = np.abs(reft - m).sum((-2, -1))
+    Ef = E.reshape(ny, nx, n * n)
+    idx = np.argmin(Ef, axis=-1)
+    out = f.astype(F32)
+    out[..., 0] += (idx % n - r).astype(F32)
+    out[..., 1] += (idx // n - r).astype(F32)
+    if return_margin:
+        srt = np.sort(Ef, axis=-1)
+        return out, (srt[..., 1] - srt[..., 0]) / np.maximum(np.abs(srt[..., 0]), 1e-12)
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------
 # ICA — ICA.py:78-481
 # --------------------------------------------------------------------------------------------------------------

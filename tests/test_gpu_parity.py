@@ -197,6 +197,37 @@ def test_ica_and_bm_per_tile_size(alcases, ts):
         assert np.array_equal(host(flow), c["bm1_%d" % ts])
 
 
+def test_ica_gradients_on_the_fly_equal_gradient_planes():
+    """ts 32 on a level that is a whole number of tiles: the kernel re-forms gradx / grady from the reference level instead
+    of reading the planes init_ica wrote — bit-identical flows; planes that are not init_ica's own are always read."""
+    from handheld_super_resolution import ICA
+    rng = np.random.default_rng(11)
+    for (ny, nx) in [(2, 3), (5, 4)]:
+        h, w = ny * 32, nx * 32
+        ref = rng.random((h, w)).astype(np.float32)
+        mov = (np.roll(ref, (1, -1), (0, 1)) + 0.02 * rng.random((h, w))).astype(np.float32)
+        cfg = attr_cfg(tile_sizes=[32], search_radii=[1])
+        flow0 = rng.uniform(-1.5, 1.5, (ny, nx, 2)).astype(np.float32)
+        refd, movd = dev(ref), dev(mov)
+        gx, gy, hess = ICA.init_ica(refd, 32, cfg)
+        assert gx._hhsr_grad_of == gy._hhsr_grad_of
+        out = {}
+        for mode in (True, False):
+            ICA.ON_THE_FLY_GRADIENTS = mode
+            try:
+                flow = dev(flow0)
+                ICA.align_lvl_ica(refd, gx, gy, hess, movd, flow, 0, cfg)
+                out[mode] = host(flow)
+            finally:
+                ICA.ON_THE_FLY_GRADIENTS = True
+        assert np.array_equal(out[True], out[False])
+        assert np.abs(out[True] - flow0).max() > 1e-3
+        # user-supplied gradient planes (here: doubled) must be honoured, not replaced by central differences
+        flow = dev(flow0)
+        ICA.align_lvl_ica(refd, gx * 2, gy * 2, hess, movd, flow, 0, cfg)
+        assert not np.array_equal(host(flow), out[True])
+
+
 @pytest.mark.parametrize("mode", ["nearest", "bilinear", "bicubic"])
 def test_upscale_modes(alcases, mode):
     from handheld_super_resolution import alignment as AL
@@ -221,6 +252,33 @@ def test_bm_l2_exact_vs_oracle_random():
         flow = dev(flow0)
         BM.align_lvl_block_matching_L2(dev(ref), None, dev(mov), flow, 0, cfg)
         assert np.array_equal(host(flow), want)
+
+
+def test_bm_l1_intended_search_vs_oracle():
+    """block_matching.tuning.l1_compat = false: the SAD search the reference intends (hhsr_bm_l1_search) — integer
+    offsets bit-exact against the oracle's restatement; the default (compat) path stays rint(flow)."""
+    import warnings
+    import hhsr_oracle as O
+    from handheld_super_resolution import block_matching as BM
+    rng = np.random.default_rng(5)
+    for ts, r in [(16, 4), (32, 2), (64, 4)]:
+        ny, nx = 3, 4
+        ref = rng.random((ny * ts, nx * ts)).astype(np.float32)
+        mov = np.roll(ref, (1, -2), (0, 1))[:, :nx * ts - 3].copy() + 0.05 * rng.random((ny * ts, nx * ts - 3)).astype(np.float32)
+        flow0 = rng.uniform(-3, 3, (ny, nx, 2)).astype(np.float32)
+        want, margin = O.bm_l1_intended(ref, mov, flow0, ts, r, return_margin=True)
+        assert margin.min() > 1e-9                      # no ties in the fixture: the argmin is well defined
+        cfg = attr_cfg(tile_sizes=[ts], search_radii=[r])
+        cfg.block_matching.tuning["l1_compat"] = False
+        flow = dev(flow0)
+        BM.align_lvl_block_matching_L1(dev(ref), dev(mov), flow, 0, cfg)
+        assert np.array_equal(host(flow), want), (ts, r)
+        cfg.block_matching.tuning["l1_compat"] = True
+        flow = dev(flow0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            BM.align_lvl_block_matching_L1(dev(ref), dev(mov), flow, 0, cfg)
+        assert np.array_equal(host(flow), O.bm_l1_compiled(flow0))
 
 
 # ------------------------------------------------------------------------------------------------ kernels

@@ -18,8 +18,8 @@ def main():
     from torch.profiler import ProfilerActivity, profile
     wl = bench.WORKLOADS["20x12MP_s2"]
     n, H, W, scale = wl["n"], wl["H"], wl["W"], wl["scale"]
-    cfg = bench.make_config(scale, H, W)
     burst_dev, _ = synth_burst(n, H, W, seed=0, device="cuda", as_numpy=False)
+    cfg = bench.make_config(scale, H, W, burst_dev[0].mean().item())
     burst_host = torch.empty((n, H, W), dtype=torch.float32).pin_memory()
     burst_host.copy_(burst_dev)
     del burst_dev

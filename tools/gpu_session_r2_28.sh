@@ -1,0 +1,14 @@
+run() {
+python - <<PY
+import json
+l=[x for x in open("gpurun_out/bench_r2_$1.json").read().splitlines() if x.startswith("{")]
+d=json.loads(l[-1]); e=d["e2e"]; print("$1 ms", round(d["ms_per_step"],3), "e2e", round(e["ms_per_step"],3), "lat", round(e["single_burst_latency_ms"],3), "u16", round(e["uint16_raw"]["ms_per_step"],3), "u16->u8", round(e["uint16_in_uint8_out"]["ms_per_step"],3))
+PY
+grep "host ms" gpurun_out/bench_r2_$1.err | awk 'NR==1 || NR==5' | cut -c1-200
+}
+for i in 1 2 3 4; do
+HHSR_BENCH_SAMPLER=off HHSR_BENCH_TRACE=1 timeout 600 python bench.py --steps 15 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2_offs$i.json 2> gpurun_out/bench_r2_offs$i.err; run offs$i
+done
+for i in 1 2 3 4; do
+HHSR_BENCH_NOGC=1 HHSR_BENCH_TRACE=1 timeout 600 python bench.py --steps 15 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2_nogc$i.json 2> gpurun_out/bench_r2_nogc$i.err; run nogc$i
+done
