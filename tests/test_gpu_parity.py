@@ -615,6 +615,41 @@ def test_main_uint16_burst_equals_float_burst():
         assert torch.equal(torch.nan_to_num(out_f), torch.nan_to_num(o))
 
 
+def test_back_to_back_host_bursts_share_the_staging_ring():
+    """Several DIFFERENT bursts enqueued back to back from host memory, nothing synchronised in between: the staging ring
+    keeps its position across bursts (slots of burst i are reused by burst i + 1 while burst i is still running) and
+    main() bounds the bursts in flight — every result must equal the same burst run from device-resident frames.  A ring
+    of 3 + batch - 1 slots is shorter than a burst, so slots are also reused inside one burst; float32 and uint16 inputs."""
+    from handheld_super_resolution import main, super_resolution as SR
+    from handheld_super_resolution.synthetic import synth_burst
+    kw = dict(scale=2, tile_size=16, tile_sizes=[16, 16, 8], factors=[1, 2, 2], metrics=["L2", "L2", "L2"], search_radii=[2, 4, 4])
+    cfg = attr_cfg(**kw)
+    cfg.exif.white_balance = [1.0, 1.0, 1.0, 0.0]
+    cfg.exif.black_levels, cfg.exif.white_level = [64, 64, 64, 64], 4095
+    bursts = [synth_burst(7, 96, 128, seed=20 + i, max_shift=2.0, quantize_bits=12)[0] for i in range(4)]
+    counts = [np.round(b * (4095 - 64) + 64).astype(np.uint16) for b in bursts]
+    import hhsr_oracle as O
+    fbursts = [O.normalize_raw(c, CFA, [64] * 4, 4095, cfg.exif.white_balance) for c in counts]
+    want = []
+    for fb in fbursts:
+        d = torch.from_numpy(fb).cuda()
+        want.append(main(d[0], d[1:], cfg, merge_batch_size=3)[0].clone())
+    torch.cuda.synchronize()
+    slots, SR.FrameFeeder.SLOTS = SR.FrameFeeder.SLOTS, 3
+    try:
+        pinned = [torch.from_numpy(fb).pin_memory() for fb in fbursts]
+        pinned16 = [torch.from_numpy(c.view(np.int16)).view(torch.uint16).pin_memory() for c in counts]
+        for rep in range(2):
+            got = [main(p[0], p[1:], cfg, merge_batch_size=3)[0] for p in pinned]            # no sync between the bursts
+            got16 = [main(p[0], p[1:], cfg, merge_batch_size=3)[0] for p in pinned16]
+            torch.cuda.synchronize()
+            for w, g, g16 in zip(want, got, got16):
+                assert torch.equal(torch.nan_to_num(w), torch.nan_to_num(g))
+                assert torch.equal(torch.nan_to_num(w), torch.nan_to_num(g16))
+    finally:
+        SR.FrameFeeder.SLOTS = slots
+
+
 @pytest.mark.parametrize("scale", [2, 1.5])
 def test_merge_init_equals_accumulate_into_zeros(stage, scale):
     """merge(init=True) on garbage-filled accumulators == merge() on zero-filled ones, bit for bit (fast path and

@@ -88,9 +88,14 @@ ALGORITHMIC = {
     "robustness_kernel": ("fused robustness", (7 * 48 + 36 + 48) * 1e6),
     "local_min5": ("5x5 minimum", 96e6),
     "bm_l2_tiled32": ("L2 block matching, level 1 (2852 tiles)", 2852 * (40 * 40 + 32 * 32) * 4),
+    "ica32_grad": ("ICA level 0 (11750 tiles), gradients re-formed in the kernel (round 2b)", 2 * 48e6),
     "ica32_kernel": ("ICA level 0 (11750 tiles)", 4 * 48e6),
     "estimate_kernels_kernel": ("kernel estimation", 96e6),
+    "gauss_downsample_stream": ("pyramid level 0 -> 1, column-streaming kernel (round 2b)", 48e6 + 12e6),
     "gauss_downsample": ("pyramid level 0 -> 1", 48e6 + 12e6),
+    "grey_rows_forward": ("grey image pass 1: row pairs forward, pruned store (round 2b)", 48e6 + 3000 * 1008 * 8),
+    "grey_cols": ("grey image pass 2: columns forward + band mask + inverse (round 2b)", 2 * 3000 * 1008 * 8),
+    "grey_rows_inverse": ("grey image pass 3: rows inverse (round 2b)", 3000 * 1008 * 8 + 48e6),
     "guide_stats": ("guide image + local stats", 48e6 + 36e6),
     "grey_band_mask": ("band mask on the half spectrum", 48e6),
     "accumulate_ref": ("merge_ref + divide", 48e6 * 48 + 12e6 * 8),
