@@ -83,6 +83,7 @@ def merge():
 
 # algorithmic bytes of one launch on a 12 MP frame at scale 2: what the stage must move at least
 ALGORITHMIC = {
+    "merge_finish": ("merge, whole burst: 19 comp frames + reference frame + divide in one pass (round 2b)", 48e6 * 12 + 19 * (12e6 * 12 + 94 * 125 * 8) + 12e6 * 8),
     "accumulate_pow2_batch": ("merge, 4 frames per pass", 48e6 * 48 + 4 * 12e6 * 12),
     "accumulate_pow2_kernel": ("merge, 1 frame per pass", 48e6 * 48 + 12e6 * 12),
     "robustness_kernel": ("fused robustness", (7 * 48 + 36 + 48) * 1e6),
