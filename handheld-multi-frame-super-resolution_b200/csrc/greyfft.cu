@@ -37,7 +37,13 @@ static void ensure_smem(Kernel kernel, std::atomic<unsigned long long> &done) {
     done.fetch_or(bit, std::memory_order_relaxed);
 }
 
-constexpr int kRowThreads = 128, kRowCtas = 4, kColThreads = 512;
+#ifndef HHSR_GREY_ROW_CTAS
+#define HHSR_GREY_ROW_CTAS 4
+#endif
+#ifndef HHSR_GREY_ROW_THREADS
+#define HHSR_GREY_ROW_THREADS 128
+#endif
+constexpr int kRowThreads = HHSR_GREY_ROW_THREADS, kRowCtas = HHSR_GREY_ROW_CTAS, kColThreads = 512;
 constexpr size_t kMaxSmem = 227 * 1024;
 
 // tw[k] = e^{-2 pi i k / n} rounded from float64; ppos_of_k: physical (padded) shared-memory position of frequency k in the

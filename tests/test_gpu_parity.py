@@ -785,6 +785,26 @@ def test_main_medium_against_golden():
     assert np.abs(np.nanmean(out.astype(np.float64), axis=(0, 1)) - m["out_mean"]).max() < 1e-6
 
 
+def assert_image_close(got, want, den, name):
+    """Whole-image comparison with the oracle: identical NaN set; |got - want| < PIPE_TOL wherever the oracle's own
+    denominator is a normal float32; where it is SUBNORMAL (a channel fed only by far taps of a very narrow kernel: den
+    is a few 1.4e-45 quanta and the reference's own value is rounding noise of ~quanta/den) the tolerance is widened by 8
+    quanta relative to that denominator — nothing is masked out.  Records how many entries sit in that regime."""
+    assert got.shape == want.shape
+    assert np.array_equal(np.isnan(got), np.isnan(want)), name
+    fin = np.isfinite(want)
+    d = np.abs(got.astype(np.float64) - want.astype(np.float64))[fin]
+    dn = np.asarray(den, np.float64)[fin]
+    tol = PIPE_TOL + 8 * 1.4e-45 / np.maximum(dn, 1.4e-45)
+    sub = dn < 1e-30
+    record("%s_subnormal_den_entries" % name, [int(sub.sum()), int(fin.sum())])
+    assert sub.mean() < 1e-2, name
+    assert (d < tol).all(), (name, float(d[~sub].max()), float((d - tol).max()))
+    worst = float(d[~sub].max()) if (~sub).any() else 0.0
+    record(name, worst)
+    assert worst < PIPE_TOL, name
+
+
 def test_main_matches_oracle_other_configs():
     """Configs the goldens do not cover, against the pinned oracle: scale 1.5, iso kernel, hard threshold,
     robustness off."""
@@ -799,15 +819,7 @@ def test_main_matches_oracle_other_configs():
         want, dbg = O.main(burst[0], burst[1:], plain_cfg(**kw))
         out, _ = main(burst[0], burst[1:], attr_cfg(**kw))
         got = host(out)
-        # A channel fed only by far taps of a very narrow kernel (hard threshold: k1 = 0.125 px) is normalised from
-        # SUBNORMAL float32 sums in the reference (den of a few 1.4e-45 quanta): its value is rounding noise there.
-        # Those pixels (a handful per image) are excluded; everything else, and the NaN set, must match.
-        noise = dbg["den"] < 1e-30
-        assert noise.mean() < 1e-2
-        got = np.where(noise & np.isfinite(want), want, got)
-        d = maxdiff(got, want)
-        record("main_vs_oracle_%s" % list(over.items())[0][1], d)
-        assert d < PIPE_TOL, over
+        assert_image_close(got, want, dbg["den"], "main_vs_oracle_%s" % list(over.items())[0][1])
 
 
 def test_main_edge_cases_against_oracle():
@@ -826,12 +838,7 @@ def test_main_edge_cases_against_oracle():
         want, dbg = O.main(burst[0], burst[1:], plain_cfg(**k))
         out, _ = main(burst[0], burst[1:], attr_cfg(**k))
         got = host(out)
-        assert got.shape == want.shape
-        noise = dbg["den"] < 1e-30
-        got = np.where(noise & np.isfinite(want), want, got)
-        d = maxdiff(got, want)
-        record("main_edge_%s" % name, d)
-        assert d < PIPE_TOL, name
+        assert_image_close(got, want, dbg["den"], "main_edge_%s" % name)
 
 
 def test_properties_full_size():
