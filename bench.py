@@ -483,11 +483,6 @@ def run_cuda_arm(args, wl, wl_name):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps, t0, t1
 
-    if os.environ.get("HHSR_BENCH_NOGC"):
-        import gc
-        gc.collect()
-        gc.freeze()
-        gc.disable()
     def warm(fn):
         """W untimed steps (at least 3), then up to 8 more until a step passes without the caching allocator calling
         cudaMalloc: a leg is timed in its steady state (an allocation in the middle of a burst drains the pipeline for
@@ -497,7 +492,10 @@ def run_cuda_arm(args, wl, wl_name):
         for _ in range(8):
             before = torch.cuda.memory_stats().get("num_device_alloc", 0)
             fn()
-            if torch.cuda.memory_stats().get("num_device_alloc", 0) == before:
+            grew = torch.tensor([float(torch.cuda.memory_stats().get("num_device_alloc", 0) != before)], device="cuda")
+            if world > 1:       # every rank must run the same number of steps (they contain the exchange)
+                dist.all_reduce(grew, op=dist.ReduceOp.MAX)
+            if grew.item() == 0.0:
                 break
 
     warm(step_resident)
