@@ -148,12 +148,22 @@ FFT_HD c32 ldc(const c32 *p) {
     return *p;
 #endif
 }
+// Bulk data (image rows, spectra) is read once: streaming loads (evict-first) keep it from pushing the twiddle and
+// digit-reversal tables, which every butterfly gathers from, out of L1.
 FFT_HD f4 ld4(const float *p) {   // 16-byte aligned
 #if defined(__CUDA_ARCH__)
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(p));
     return f4{v.x, v.y, v.z, v.w};
 #else
     return f4{p[0], p[1], p[2], p[3]};
+#endif
+}
+FFT_HD c32 ldc_stream(const c32 *p) {
+#if defined(__CUDA_ARCH__)
+    const float2 v = __ldcs(reinterpret_cast<const float2 *>(p));
+    return c32{v.x, v.y};
+#else
+    return *p;
 #endif
 }
 FFT_HD int ldi(const int *p) {
@@ -452,7 +462,7 @@ FFT_HD void rows_scatter_half_spectra(c32 *s, const int *ppos_of_k, const c32 *s
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             const int k = k0 + u * nt;
-            if (k < KX) A[u] = ldc(specA + k), B[u] = ldc(specB + k), p[u] = ldi(ppos_of_k + k), pn[u] = ldi(ppos_of_k + (k == 0 ? 0 : W - k));
+            if (k < KX) A[u] = ldc_stream(specA + k), B[u] = ldc_stream(specB + k), p[u] = ldi(ppos_of_k + k), pn[u] = ldi(ppos_of_k + (k == 0 ? 0 : W - k));
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
@@ -494,7 +504,7 @@ FFT_HD void cols_load_tile(c32 *s, const c32 *spec, long long pitch, int H, int 
         c32 v[kB];
 #pragma unroll
         for (int u = 0; u < kB; ++u)
-            if (yb + u * step < H) v[u] = ldc(spec + (long long)(yb + u * step) * pitch + c0 + c);
+            if (yb + u * step < H) v[u] = ldc_stream(spec + (long long)(yb + u * step) * pitch + c0 + c);
 #pragma unroll
         for (int u = 0; u < kB; ++u)
             if (yb + u * step < H) s[c * Hp + phys<PAD>(yb + u * step)] = v[u];
