@@ -51,6 +51,24 @@ def _throttle_host(device):
         q.pop(0).synchronize()
 
 
+MAX_FRAMES_IN_FLIGHT = int(os.environ.get("HHSR_MAX_FRAMES_IN_FLIGHT", "10"))
+
+
+def _frame_enqueued(device, k):
+    """Same idea at frame granularity, inside the frame loop: the host never runs more than MAX_FRAMES_IN_FLIGHT comp
+    frames (~95 launches each) ahead of the compute stream, which keeps the driver's launch queues from ever filling up
+    (0 switches it off).  The host needs 0.45 ms to enqueue a frame the GPU works 0.95 ms on, so it waits here often — on
+    an event, not inside a launch call."""
+    if MAX_FRAMES_IN_FLIGHT <= 0:
+        return
+    q = _INFLIGHT.setdefault(("frames", device.index), [])
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    q.append(ev)
+    while len(q) > MAX_FRAMES_IN_FLIGHT:
+        q.pop(0).synchronize()
+
+
 def _burst_enqueued(device):
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(device))
@@ -326,6 +344,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
             if accumulate_r:
                 add_many(accumulated_r, [r])
             feed.release(k)
+            _frame_enqueued(dev, k)
             continue
         pending.append((k, cuda_img, flow, covs, r))
         if len(pending) == batch_size or k == len(ids) - 1:
@@ -347,6 +366,7 @@ def main(ref_img, comp_imgs, config, frame_ids=None, reduce_fn=None, accumulator
             pending = []
         if debug_mode:
             debug_dict["robustness"].append(r.cpu().numpy())
+        _frame_enqueued(dev, k)
 
     # the one reduction point of the pipeline (frame-sharded runs): reduce_fn sums the accumulators across ranks and
     # may hand back the slice of output rows this rank has to normalise plus a callable that re-assembles the image
