@@ -278,20 +278,28 @@ class RowShardedMerge:
         return out
 
 
-def broadcast_reference_frame(ref_img, group=None):
+def broadcast_reference_frame(ref_img, config, group=None):
     """Every rank needs the reference frame.  When it lives in host memory, rank 0 uploads it once and NCCL broadcasts it
     over NVLink (48 MB at 12 MP) instead of every rank pulling its own copy through the host's PCIe complex — with 8
     ranks that is 7 frames less of host-to-device traffic per burst.  Input distribution only: the merge path still has
-    its single exchange point.  Device-resident frames pass through."""
+    its single exchange point.  Device-resident frames pass through.
+
+    Rank 0 stages the frame like main() stages every host frame — on the copy stream, through the persistent staging ring
+    (FrameFeeder), so the upload of burst i + 1's reference frame overlaps the compute of burst i — and broadcasts the
+    NORMALISED float32 frame (uint16 sensor counts are normalised on rank 0 only; the other ranks receive exactly what
+    rank 0 computes with)."""
     if isinstance(ref_img, torch.Tensor) and ref_img.is_cuda:
         return ref_img
-    from .super_resolution import _host_tensor
+    from .super_resolution import FrameFeeder, _host_tensor
+    dev = torch.device("cuda", torch.cuda.current_device())
     host = _host_tensor(ref_img)
-    buf = torch.empty(host.shape, dtype=host.dtype, device=torch.device("cuda", torch.cuda.current_device()))
     if dist.get_rank(group) == 0:
-        buf.copy_(host, non_blocking=True)
-    wire = buf.view(torch.uint8) if buf.dtype in (torch.uint16, torch.int16) else buf   # NCCL has no 16-bit integer type
-    dist.broadcast(wire, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        feed = FrameFeeder([host], [0], config, dev, role="ref")
+        buf = feed.get(0).clone()          # the frame outlives its staging slot
+        feed.release(0)
+    else:
+        buf = torch.empty(host.shape, dtype=torch.float32, device=dev)
+    dist.broadcast(buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     return buf
 
 
@@ -315,7 +323,7 @@ def main_sharded(ref_img, comp_imgs, config, group=None, mode=None):
     ids = shard_frames(len(comp_imgs), rank, world)
     ahead = None
     if world > 1:
-        ref_img = broadcast_reference_frame(ref_img, group)
+        ref_img = broadcast_reference_frame(ref_img, config, group)
         ahead = max(1, min(len(ids), int(os.environ.get("HHSR_SHARD_ALIGN_AHEAD", "3"))))   # few frames per rank: run their chains together
     if mode == "rows" and world > 1:
         H, W = ref_img.shape
