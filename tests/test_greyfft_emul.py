@@ -35,6 +35,12 @@ def test_factorization(emul):
         evens = [r for r in got if r % 2 == 0]
         assert got[:len(evens)] == sorted(evens, reverse=True) and all(r % 2 for r in got[len(evens):]), got
         assert pad.value == (0 if got[-1] % 2 else 1)
+    # common sensor formats: which run the native passes (three stages each) ...
+    for n in (4000, 3000, 4032, 3024, 6000, 4608, 3456, 8192, 6144):
+        assert emul.emul_factorize(n, radix, C.byref(pad)) == 3, n
+    # ... and which keep the cuFFT route (19 | 5472, 3648; 17 | 4624; 31 | 3472; 13 | 6240, 4160)
+    for n in (5472, 3648, 4624, 3472, 6240, 4160):
+        assert emul.emul_factorize(n, radix, C.byref(pad)) == -1, n
     for n in (1, 740, 170, 22, 13):          # a prime factor above 7: the caller keeps the cuFFT route
         assert emul.emul_factorize(n, radix, C.byref(pad)) == -1
 
