@@ -61,7 +61,8 @@ FFT_HD int phys(int i) {
 // ---- host: choose the radices.  Fewest stages; among those prefer a solution with an odd radix (it runs last and
 // needs no padding), then the smallest largest radix (register pressure), then the largest smallest radix.
 namespace detail {
-constexpr int kRadices[18] = {32, 25, 24, 21, 20, 16, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+constexpr int kNumRadices = 22;
+constexpr int kRadices[kNumRadices] = {32, 25, 24, 21, 20, 19, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
 struct Search {
     int best[kMaxStages], nbest;
     long long best_score;
@@ -78,7 +79,7 @@ struct Search {
             return;
         }
         if (depth >= kMaxStages || (nbest && depth + 1 > nbest)) return;
-        for (int i = start; i < 18; ++i)
+        for (int i = start; i < kNumRadices; ++i)
             if (rem % kRadices[i] == 0) cur[depth] = kRadices[i], go(rem / kRadices[i], depth + 1, i);
     }
 };
@@ -88,7 +89,7 @@ inline bool make_plan(int n, Plan &p) {
     p.n = n, p.count = 0, p.pad = 0;
     if (n < 2 || n > 65536) return false;
     int rem = n;
-    const int primes[4] = {2, 3, 5, 7};
+    const int primes[8] = {2, 3, 5, 7, 11, 13, 17, 19};
     for (int q : primes)
         while (rem % q == 0) rem /= q;
     if (rem != 1) return false;
@@ -228,6 +229,36 @@ FFT_HD void dft_small(c32 (&v)[R]) {
     }
 }
 
+// Prime radices 11, 13, 17, 19 (frame sizes such as 6240 x 4160 or 5472 x 3648): the direct transform on the symmetric
+// and antisymmetric pairs, X_k = v_0 + sum_n cos(2 pi k n / R) (v_n + v_{R-n}) -+ i sum_n sin(2 pi k n / R) (v_n - v_{R-n})
+// and X_{R-k} its mirror — (R-1)^2 real multiply-adds, about what a radix-16 butterfly costs for R = 13.
+template <int R, bool INV>
+FFT_HD void dft_prime(c32 (&v)[R]) {
+    constexpr int HALF = (R - 1) / 2;
+    c32 p[HALF], m[HALF];
+    c32 x0 = v[0];
+    static_for<HALF>([&](auto N) {
+        constexpr int n = decltype(N)::value;
+        p[n] = cadd(v[n + 1], v[R - 1 - n]), m[n] = csub(v[n + 1], v[R - 1 - n]);
+        x0 = cadd(x0, p[n]);
+    });
+    c32 out[R];
+    out[0] = x0;
+    static_for<HALF>([&](auto K) {
+        constexpr int k = decltype(K)::value + 1;
+        c32 a = v[0], b = c32{0.f, 0.f};
+        static_for<HALF>([&](auto N) {
+            constexpr int n = decltype(N)::value + 1;
+            constexpr float c = Wtab<R>::c[(k * n) % R], s = Wtab<R>::s[(k * n) % R];
+            a = c32{a.x + c * p[n - 1].x, a.y + c * p[n - 1].y};
+            b = c32{b.x + s * m[n - 1].x, b.y + s * m[n - 1].y};
+        });
+        b = rot90<INV>(b);
+        out[k] = cadd(a, b), out[R - k] = csub(a, b);
+    });
+    static_for<R>([&](auto T) { v[decltype(T)::value] = out[decltype(T)::value]; });
+}
+
 // multiplication by the compile-time twiddle e^{-+ 2 pi i N / R}
 template <int R, int N, bool INV>
 FFT_HD c32 mul_const(c32 a) {
@@ -278,6 +309,7 @@ FFT_HD void dft(c32 (&v)[R]) {
     else if constexpr (R == 24) dft_composite<8, 3, INV>(v);
     else if constexpr (R == 25) dft_composite<5, 5, INV>(v);
     else if constexpr (R == 32) dft_composite<8, 4, INV>(v);
+    else if constexpr (R == 11 || R == 13 || R == 17 || R == 19) dft_prime<R, INV>(v);
     else dft_small<R, INV>(v);
 }
 
@@ -353,10 +385,14 @@ FFT_HD void run_stage(c32 *x, const c32 *tw, const Plan &p, int s, int tid, int 
     case 8: stage_loop<8, INV, PAD>(x, tw, d, nb, tid, nt); break;
     case 9: stage_loop<9, INV, PAD>(x, tw, d, nb, tid, nt); break;
     case 10: stage_loop<10, INV, PAD>(x, tw, d, nb, tid, nt); break;
+    case 11: stage_loop<11, INV, PAD>(x, tw, d, nb, tid, nt); break;
     case 12: stage_loop<12, INV, PAD>(x, tw, d, nb, tid, nt); break;
+    case 13: stage_loop<13, INV, PAD>(x, tw, d, nb, tid, nt); break;
     case 14: stage_loop<14, INV, PAD>(x, tw, d, nb, tid, nt); break;
     case 15: stage_loop<15, INV, PAD>(x, tw, d, nb, tid, nt); break;
     case 16: stage_loop<16, INV, PAD>(x, tw, d, nb, tid, nt); break;
+    case 17: stage_loop<17, INV, PAD>(x, tw, d, nb, tid, nt); break;
+    case 19: stage_loop<19, INV, PAD>(x, tw, d, nb, tid, nt); break;
     case 20: stage_loop<20, INV, PAD>(x, tw, d, nb, tid, nt); break;
     case 21: stage_loop<21, INV, PAD>(x, tw, d, nb, tid, nt); break;
     case 24: stage_loop<24, INV, PAD>(x, tw, d, nb, tid, nt); break;

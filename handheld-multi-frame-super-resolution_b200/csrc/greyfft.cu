@@ -134,7 +134,7 @@ struct GreyLayout {
 static int grey_layout(int H, int W, GreyLayout &g) {
     if (H < 8 || W < 8 || (H & 1)) return unsupported("grey FFT: needs an even number of rows and at least 8 x 8 pixels");
     if (!fft::make_plan(W, g.pw) || !fft::make_plan(H, g.ph))
-        return unsupported("grey FFT: image sizes must factor into 2, 3, 5 and 7");
+        return unsupported("grey FFT: image sizes must factor into primes up to 19");
     g.KX = fft::kept_columns(W);
     g.smem_rows = (size_t)fft::phys_len(W, g.pw.pad) * sizeof(c32);
     if (g.smem_rows > kMaxSmem) return unsupported("grey FFT: row too long for shared memory");

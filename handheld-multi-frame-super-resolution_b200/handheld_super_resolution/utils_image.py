@@ -14,7 +14,7 @@ GREY_FFT_NATIVE = True   # False: always take the cuFFT route (tests compare the
 
 def _grey_plan(h, w, device):
     """Twiddle / digit-reversal tables of the library's own grey-image FFT for an h x w frame, built once per shape and
-    device; None when the sizes do not factor into 2, 3, 5, 7 (those frames take the cuFFT route)."""
+    device; None when a size has a prime factor above 19 (those frames take the cuFFT route)."""
     key = (device.index, h, w)
     if key not in _GREY_PLANS:
         L = _lib.lib()
@@ -35,7 +35,7 @@ def _grey_plan(h, w, device):
 def compute_grey_images(img, method):
     """Raw -> grey (utils_image.py:58-115).
 
-    "FFT": the ideal half-band low-pass of Alg. 3.  Frames whose sizes factor into 2, 3, 5, 7 (4000 x 3000, 4032 x 3024, 8192 x 6144, ...) go
+    "FFT": the ideal half-band low-pass of Alg. 3.  Frames whose sizes factor into primes up to 19 (4000 x 3000, 4032 x 3024, 5472 x 3648, 8192 x 6144, ...) go
     through the library's own three shared-memory FFT passes (hhsr_grey_fft: rows forward, columns forward + band mask +
     inverse, rows inverse; only the quarter of the spectrum the mask keeps is ever stored).  Other sizes: cuFFT
     (torch.fft.rfft2 / irfft2) around the in-place band-mask kernel hhsr_grey_band_mask — the reference's fftshift +

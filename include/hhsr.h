@@ -47,7 +47,7 @@ int hhsr_grey_band_mask(float *spec, int H, int W, long long stride_y, long long
 /* ---- grey image, Alg. 3, as a whole (utils_image.py:82-100: fft2, fftshift, four masked fills, ifftshift, ifft2,
  * .real) with the library's own shared-memory FFT passes: rows forward (two real rows per complex transform, only the
  * W/4 + 1 half-spectrum columns the mask keeps are stored), columns (forward, band mask, inverse in one pass), rows
- * inverse.  Sizes must factor into 2, 3, 5, 7 with H even (HHSR_E_UNSUPPORTED otherwise: the caller keeps the cuFFT
+ * inverse.  Sizes must factor into primes up to 19 with H even (HHSR_E_UNSUPPORTED otherwise: the caller keeps the cuFFT
  * route with hhsr_grey_band_mask for those).
  *   hhsr_grey_fft_sizes: bytes of the two caller-owned device buffers for an H x W image (host pointers out);
  *   hhsr_grey_fft_plan:  fills `plan` (twiddle tables rounded from float64, digit-reversal tables) once per (H, W);

@@ -71,7 +71,8 @@ def test_grey_fft_odd_sizes():
         assert d < 2e-6, (shape, d)
 
 
-@pytest.mark.parametrize("shape", [(48, 64), (96, 128), (120, 168), (350, 360), (750, 1000), (1000, 1400), (2048, 2560)])
+@pytest.mark.parametrize("shape", [(48, 64), (96, 128), (120, 168), (350, 360), (750, 1000), (1000, 1400), (2048, 2560),
+                                   (66, 104), (208, 312), (1040, 1560), (912, 1368), (578, 1156)])   # prime radices 11, 13, 19, 17
 def test_grey_fft_native_passes(shape):
     """The library's own FFT passes (hhsr_grey_fft: rows forward, columns + band mask, rows inverse) against the oracle
     (float64 numpy restatement of utils_image.py:82-100) and against the cuFFT route around hhsr_grey_band_mask."""

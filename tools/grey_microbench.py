@@ -15,7 +15,8 @@ def main():
     from handheld_super_resolution.synthetic import synth_burst
     iters = int(os.environ.get("ITERS", "20"))
     res = {}
-    for (H, W) in [(3000, 4000), (6144, 8192)]:
+    sizes = [tuple(int(v) for v in x.split("x")) for x in os.environ.get("SIZES", "3000x4000,6144x8192").split(",")]
+    for (H, W) in sizes:
         burst, _ = synth_burst(2, H, W, seed=0, device="cuda", as_numpy=False)
         img = burst[1]
 
