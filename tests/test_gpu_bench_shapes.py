@@ -23,7 +23,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import CFA, WB, GOLDEN, attr_cfg, load
+from helpers import GOLDEN, attr_cfg, load
 
 pytestmark = pytest.mark.gpu
 

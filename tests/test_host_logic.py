@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from helpers import attr_cfg, curves
+from helpers import curves
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 

@@ -1,6 +1,5 @@
 """Per-step times of the host-to-host legs of bench.py (float32 and uint16 bursts), to see whether a slow average is a
 few stalled steps or a uniformly slow pipeline.  Usage: python tools/e2e_steps.py [merge_batch]"""
-import json
 import os
 import sys
 import time
